@@ -1,0 +1,152 @@
+/*
+ * vqgnn.h — C-ABI of libvqgnn.so: the B200 (sm_100a) kernels behind VQ-GNN's hot path.
+ *
+ * The reference (devnkong/VQ-GNN) is pure Python and has no FFI; its boundary for this path is the
+ * Python class surface.  Each entry point below replaces the body of one reference
+ * function; the Python modules in vq_gnn_b200/ keep the reference's class names and signatures and
+ * bind these symbols with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*;
+ *   - no allocation, no ownership transfer: the caller passes outputs and workspaces;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), stateless, thread-safe;
+ *   - return 0 on success, a negative VQGNN_ERR_* otherwise; vqgnn_last_error() gives the text;
+ *   - all floating point is fp32 (moments are accumulated in fp64), indices int32, codes int16.
+ *
+ * Layouts (HBM)
+ *   x / g / y      row-major [rows, ld] fp32; branch k owns columns [k*D, (k+1)*D) of x and
+ *                  [k*Dg, (k+1)*Dg) of g (Dg = D, or D+1 for the v1 GAT "add_flag" quantiser);
+ *   codebooks      E (whitened, `_embedding`), W (`_ema_w`), O (de-whitened, `_embedding_output`):
+ *                  [nb, M, Wp] with Wp = 4*ceil(W/4), W = D + Dg (feature part first, gradient part after);
+ *   sizes          `_ema_cluster_size` [nb, M];
+ *   codes          node -> codeword table [N, nb] int16 (one row = all branches of a node; the
+ *                  reference keeps nb separate `c_indices[N]` buffers, vq_gnn_v2/models.py:27-28);
+ *   stats          per-codeword accumulator [nb, M, Wp + 4]: Wp sums, then count, then 3 pad words;
+ *                  this flat buffer (plus `sums`) is what a multi-GPU run allreduces between
+ *                  vqgnn_vq_assign and vqgnn_vq_finalize.
+ */
+#ifndef VQGNN_H_
+#define VQGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQGNN_ABI_VERSION 1
+
+#define VQGNN_OK 0
+#define VQGNN_ERR_ARCH (-1)      /* device is not sm_100 */
+#define VQGNN_ERR_ARG (-2)       /* bad argument / unsupported shape */
+#define VQGNN_ERR_CUDA (-3)      /* a CUDA runtime call failed */
+#define VQGNN_ERR_WORKSPACE (-4) /* workspace too small */
+
+/* status word bits written by vqgnn_vq_finalize (read lazily by the host) */
+#define VQGNN_STATUS_BAD_INIT 1  /* some EMA cluster size is exactly 0: reference raises ValueError('Bad Init!') (vq.py:188,253) */
+
+int vqgnn_abi_version(void);
+/* 0 if `device` is compute capability 10.x, VQGNN_ERR_ARCH otherwise. */
+int vqgnn_arch_check(int device);
+const char* vqgnn_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches claim) */
+int64_t vqgnn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * VectorQuantizerEMA  (vq_gnn_v2/vq.py:160-279), all nb branches of a layer in one launch each.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Column sums and sums of squares (fp64) of x[B, C] and, if g != NULL, g[B, Cg]:
+ *   sums[0 .. C+Cg)          = sum_b v[b, c]
+ *   sums[C+Cg .. 2(C+Cg))    = sum_b v[b, c]^2
+ * Replaces the batch statistics inside BatchNorm1d.forward (vq.py:162,223) and the explicit
+ * mean/var at vq.py:216-221.  `sums` is overwritten.  In a multi-GPU run it is allreduced (sum). */
+int vqgnn_vq_moments(const float* x, int64_t ldx, const float* g, int64_t ldg, int64_t B, int C, int Cg,
+                     double* sums, void* stream);
+
+/* Turns moments into the per-column whitening affine z = v * scale + shift and updates the BatchNorm
+ * running statistics exactly as torch.nn.BatchNorm1d(affine=False) does in train mode
+ * (biased variance for normalisation, unbiased for the running update), incl. the first-update
+ * re-seeding of vq.py:216-221 (`seed_running` != 0).  If training == 0 the running statistics are
+ * used and left untouched.  Gradient columns are additionally multiplied by grad_scale0 (last column
+ * of each branch by grad_scale1 when Dg == D+1) (vq.py:224-227).
+ *   run_mean_f/run_var_f: [nb*D]; run_mean_g/run_var_g: [nb*Dg] (NULL when Cg == 0)
+ *   scale/shift: [C + Cg] outputs.  count = number of rows the moments were taken over (global); if d_count
+ *   (a device double) is not NULL it overrides `count`, so an allreduced row count needs no host sync.
+ *   nbt_f [nb] / nbt_g [nb]: BatchNorm1d.num_batches_tracked counters (int64, may be NULL), +1 in training. */
+int vqgnn_vq_whiten(const double* sums, double count, const double* d_count, int nb, int D, int Dg, int has_grad,
+                    float* run_mean_f, float* run_var_f, float* run_mean_g, float* run_var_g,
+                    float eps_f, float mom_f, float eps_g, float mom_g, float grad_scale0, float grad_scale1,
+                    int training, int seed_running, int64_t* nbt_f, int64_t* nbt_g, float* scale, float* shift,
+                    void* stream);
+
+/* Fused whitening + nearest-codeword assignment + per-codeword accumulation.
+ * For every row b and branch k: z = whiten([x_k | g_k]); code = argmin_m ||z||^2 + ||E_k[m]||^2 - 2 z.E_k[m]
+ * (that association order, fp32, lowest index wins ties: vq.py:166-171 / 230-236) using the
+ * PRE-update codebook; writes idx[b, k] ([B, nb]) and, if codes != NULL, codes[batch_idx[b]*codes_ld + k]
+ * (models.py:46,63; codes_ld = row stride of the code table, so a sub-range of branches can be updated); if stats != NULL adds z to stats[k, code, :W] and 1 to stats[k, code, Wp]
+ * (the one-hot^T @ z GEMM and column sum of vq.py:243,256 as a segmented sum).  `stats` must be zeroed
+ * by the caller (vqgnn_fill_zero).  g == NULL selects the feature-only form (feature_update, W = D).
+ * impl: 0 = exact-fp32 SIMT kernel (parity anchor), 1 = tcgen05/TMEM 3xTF32 kernel (D == 4 only). */
+int vqgnn_vq_assign(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
+                    const float* shift, const float* E, int64_t B, int nb, int M, int D, int Dg, int Wp,
+                    const int32_t* batch_idx, int16_t* codes, int64_t codes_ld, int16_t* idx, float* stats,
+                    int impl, void* stream);
+
+/* EMA + Laplace smoothing + codeword recovery (vq.py:177-200 / 242-275), one CTA per branch:
+ *   size <- decay*size + (1-decay)*count; if warm_up: size <- (size+1e-5)/(sum(size)+M*1e-5)*sum(size);
+ *   status |= BAD_INIT if any size == 0; Wm <- decay*Wm + (1-decay)*sum_z; E <- Wm/size;
+ *   O <- de-whiten(E) with the (already updated) running statistics; gradient part divided by
+ *   (grad_scale + eps); O[:, D:] <- 0 if grad_scale0 == 0.
+ * joint == 0 updates only the first D columns (feature_update). */
+int vqgnn_vq_finalize(const float* stats, int nb, int M, int D, int Dg, int Wp, int joint, double decay,
+                      int warm_up, float eps, float grad_scale0, float grad_scale1,
+                      const float* run_mean_f, const float* run_var_f, const float* run_mean_g,
+                      const float* run_var_g, float* ema_size, float* ema_w, float* E, float* O,
+                      int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Message passing, GCN / SAGE-Mean (OurGCNConv.forward = adj @ x, vq_gnn_v2/convs.py:65-101)
+ * fused with the codeword gather of vq_gnn_v2/models.py:161-173 (v2) or the A*R product that
+ * vq_gnn_v1/utils/dataloader.py:144-192 (`mapper`) materialises (v1).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Forward over R rows of the plan's CSR (see vq_gnn_b200/graph.py: BatchPlan).  For row r:
+ *   acc   = sum_e val[e] * (col[e] < B ? x[col[e], :] : feat_scale * O_k[code(node(col[e]-B), k), :D])
+ *   gqacc = sum_{tail e} rval[e] * O_k[code(...), D:2D]                   (only if rval != NULL)
+ * rows r <  B: y[r, :] = acc; gq[r, :] = gqacc; info += <x[r, :], gqacc>  (v1 info_backward, models.py:223)
+ * rows r >= B: info += <acc, O_k[code(node(r-B), k), D:2D]>               (v2 info_backward, models.py:198)
+ * *info = info_scale * info (fp64 accumulation, deterministic to fp32 rounding).
+ * C = nb*D columns.  tail_node == NULL means identity.  info/gq may be NULL.
+ * ws: vqgnn_mp_workspace_bytes() bytes, zeroed by this call. */
+size_t vqgnn_mp_workspace_bytes(void);
+int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval, int64_t R,
+                 int64_t B, const float* x, int64_t ldx, const int32_t* tail_node, const int16_t* codes,
+                 const float* O, int nb, int M, int D, int Wp, float feat_scale, float info_scale,
+                 float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws, void* stream);
+
+/* Backward of the same: for batch column j < B
+ *   dx[j, :] = sum_e bval[e] * (brow[e] < B ? dy[brow[e], :]
+ *                                           : tail_scale * (*dinfo) * O_k[code(node(brow[e]-B), k), D:2D])
+ *              + gq_scale * (*dinfo) * gq[j, :]        (if gq != NULL; v1)
+ * i.e. adj^T @ dY restricted to batch rows plus the gradient of info_backward.
+ * dinfo is a device scalar (NULL = 1). */
+int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval, int64_t B, const float* dy,
+                 int64_t lddy, const int32_t* tail_node, const int16_t* codes, const float* O, int nb,
+                 int M, int D, int Wp, float tail_scale, const float* gq, int64_t ldgq, float gq_scale,
+                 const float* dinfo, float* dx, int64_t lddx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * helpers
+ * ------------------------------------------------------------------------------------------- */
+int vqgnn_fill_zero(void* ptr, size_t bytes, void* stream);
+/* codes[N, nb] <-> nb separate c_indices[N] tables (the reference layout) */
+int vqgnn_codes_pack(const int16_t* const* h_tables, int nb, int64_t N, int16_t* codes, void* stream);
+/* L2 flush helper for benchmarks: writes `bytes` of zeros to buf */
+int vqgnn_flush_l2(void* buf, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQGNN_H_ */

@@ -1,0 +1,53 @@
+"""Shared builders for the parity tests: small seeded graphs, reference-format batches, layers."""
+import torch
+
+from vq_gnn_b200 import sampling, synth
+from vq_gnn_b200.graph import CSRAdj
+
+LAYER_KW = dict(dropout=0., num_branch=0, cluster='vq', ln_para=True, no_second_fc=True, kmeans_iter=100,
+                EMA_flag=True, split=True, kmeans_init=False, dropbranch=0, use_gcn=False, commitment_cost=0.,
+                hook=True, weight_ahead=False, transformer_flag=False)
+
+
+def layer_args(C, C_out, M, D, N, conv_type, skip=False, grad_scale=(1, 1), warm_up_flag=True, momentum=0.1):
+    """Positional argument list of LowRankGNNLayer.__init__ (vq_gnn_v2/models.py:67-70)."""
+    return [C, C_out, 0., M, D, N, 0, 'vq', True, True, 100, True, True, False, 0, skip, False, 0.,
+            list(grad_scale), True, False, warm_up_flag, momentum, conv_type, False]
+
+
+def make_graph(N, E, conv_type, version, seed=0, power_law=0.0):
+    return synth.make_graph(N, E, conv_type, version, seed=seed, power_law=power_law)
+
+
+def make_batch(g, B, version, seed=0, train=True, recovery=True):
+    gen = torch.Generator().manual_seed(seed + 1000)
+    node_idx = torch.randperm(g.N, generator=gen)[:B]
+    if version == 'v2':
+        return sampling.k_hop_batch_v2(g, node_idx, train_flag=train)
+    return sampling.collate_batch_v1(g, node_idx, train_flag=train, recovery_flag=recovery)
+
+
+def batch_to(batch_A, device):
+    out = []
+    for t in batch_A:
+        if t is None:
+            out.append(None)
+        elif isinstance(t, tuple):
+            out.append(tuple(u.to(device) for u in t))
+        else:
+            out.append(t.to(device))
+    return tuple(out)
+
+
+def to_shim_batch(batch_A, ts):
+    """Convert a v2 batch (CSRAdj) into one holding the oracle-shim SparseTensor (for the live reference)."""
+    if len(batch_A) != 3:
+        return batch_A
+    batch_idx, subset, adj = batch_A
+    row, col, val = adj.coo()
+    return batch_idx, subset, ts.SparseTensor(row=row, col=col, value=val, sparse_sizes=adj.sparse_sizes())
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))

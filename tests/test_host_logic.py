@@ -1,0 +1,108 @@
+"""CPU tests of the host-side logic: C-ABI export list, state_dict parity, plan construction."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import vq_gnn_b200 as V
+from oracle import restate
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vqgnn.h")).read()
+    names = set(re.findall(r"\b(vqgnn_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 10
+    lib = ctypes.CDLL(V._lib.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, f"declared in include/vqgnn.h but not exported: {missing}"
+    assert lib.vqgnn_abi_version() == 1
+    for n in names:   # the binding table must cover the header too
+        assert n in V._lib._SIGNATURES, n
+
+
+def test_no_cpu_fallback():
+    vq = V.VectorQuantizerEMA(16, 4, grad_normalize_scale=[1, 1])
+    with pytest.raises(V._lib.VQGNNLibraryError):
+        vq.feature_update(torch.randn(8, 4))
+    with pytest.raises(ValueError):
+        V.VectorQuantizerEMA(16, 4, grad_normalize_scale=(1, 1))      # vq.py:91-92
+
+
+@pytest.mark.parametrize("version,conv", [("v2", "GCN"), ("v2", "SAGE"), ("v2", "GAT"), ("v1", "GCN"),
+                                          ("v1", "SAGE"), ("v1", "GAT")])
+def test_state_dict_keys_and_views(version, conv):
+    torch.manual_seed(0)
+    layer = V.LowRankGNNLayer(*H.layer_args(8, 6, 16, 4, 50, conv, skip=True), version=version)
+    sd = layer.state_dict()
+    assert f"gnn_block.1.vq._embedding" in sd and "gnn_block.0.c_indices" in sd
+    W = 9 if (version == "v1" and conv == "GAT") else 8
+    assert sd["gnn_block.0.vq._embedding"].shape == (16, W)
+    assert sd["gnn_block.0.c_indices"].dtype == torch.int16
+    # per-branch buffers alias the stacked bank
+    layer.bank.O[1, 2, 3] = 5.0
+    assert float(layer.gnn_block[1].vq._embedding_output[2, 3]) == 5.0
+    # load_state_dict writes through the views
+    sd2 = {k: (v.clone() + 1 if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    layer.load_state_dict(sd2)
+    assert torch.equal(layer.bank.E[0, :, :W], sd2["gnn_block.0.vq._embedding"])
+    assert torch.equal(layer.bank.codes[:, 1], sd2["gnn_block.1.c_indices"])
+    # the oracle accepts the same state dict
+    o = restate.OracleLayer(8, 6, 16, 4, 50, conv, version, skip=True, warm_up_flag=True).load_state_dict(sd2)
+    assert torch.equal(o.vq[1]._ema_w, sd2["gnn_block.1.vq._ema_w"])
+
+
+@pytest.mark.parametrize("conv", ["GCN", "SAGE", "GAT"])
+@pytest.mark.parametrize("train,recovery", [(True, True), (True, False), (False, True)])
+def test_plan_v1_equals_mapper(conv, train, recovery):
+    """The kernel plan must encode exactly the matrix `mapper` builds (v1/utils/dataloader.py:144-192)."""
+    N, B, M = 120, 30, 8
+    g = H.make_graph(N, 400, conv, "v1", seed=3)
+    batch_A = H.make_batch(g, B, "v1", seed=3, train=train, recovery=recovery)
+    c = torch.randint(0, M, (N,), dtype=torch.short, generator=torch.Generator().manual_seed(5))
+    ref = restate.mapper_dense(batch_A, c, M, conv)
+    plan = V.graph.plan_from_v1(batch_A, conv, N, train, "cpu")
+    dense = torch.zeros(B + M, B + M)
+    deg = plan.fwd_rowptr[1:] - plan.fwd_rowptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(B), deg.long())
+    cols, vals = plan.fwd_col.long(), plan.fwd_val
+    inb = cols < B
+    dense.index_put_((rows[inb], cols[inb]), vals[inb], accumulate=True)
+    cm = c.long()[cols[~inb] - B] + B
+    dense.index_put_((rows[~inb], cm), vals[~inb], accumulate=True)
+    if plan.fwd_rval is not None:
+        dense.index_put_((cm, rows[~inb]), plan.fwd_rval[~inb], accumulate=True)
+    assert torch.allclose(dense, ref, atol=1e-6), (dense - ref).abs().max()
+    # transposed structure == in-batch block transposed
+    bt = torch.zeros(B, B)
+    bdeg = plan.bwd_rowptr[1:] - plan.bwd_rowptr[:-1]
+    bj = torch.repeat_interleave(torch.arange(B), bdeg.long())
+    bt.index_put_((plan.bwd_col.long(), bj), plan.bwd_val, accumulate=True)
+    assert torch.allclose(bt, ref[:B, :B], atol=1e-6)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_plan_v2_roundtrip(train):
+    N, B = 150, 40
+    g = H.make_graph(N, 500, "GCN", "v2", seed=1)
+    batch_idx, subset, adj = H.make_batch(g, B, "v2", seed=1, train=train)
+    plan = V.graph.plan_from_v2((batch_idx, subset, adj), "GCN", N, train, "cpu")
+    assert plan.B == B and plan.R == (subset.numel() if train else B)
+    dense = adj.to_dense()
+    rec = torch.zeros_like(dense)
+    deg = (plan.fwd_rowptr[1:] - plan.fwd_rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(plan.R), deg)
+    rec.index_put_((rows, plan.fwd_col.long()), plan.fwd_val, accumulate=True)
+    assert torch.equal(rec[:plan.R], dense[:plan.R])
+    bt = torch.zeros(plan.R, B)
+    bdeg = (plan.bwd_rowptr[1:] - plan.bwd_rowptr[:-1]).long()
+    bj = torch.repeat_interleave(torch.arange(B), bdeg)
+    bt.index_put_((plan.bwd_col.long(), bj), plan.bwd_val, accumulate=True)
+    assert torch.equal(bt, dense[:plan.R, :B])
+    assert torch.equal(plan.tail_node.long(), subset[B:])
+    # batch nodes lead the subset (vq_gnn_v2/dataloader.py:128)
+    assert torch.equal(subset[:B], batch_idx)

@@ -1,0 +1,408 @@
+"""`LowRankGNNBlock` / `LowRankGNNLayer` / `LowRankGNN` — drop-ins for vq_gnn_v{1,2}/models.py.
+
+Constructor and forward signatures, return tuples, module tree and `state_dict()` keys follow the
+reference (v2: models.py:11-63, 66-231, 234-374; v1: models.py:23-233, 236-367, 370-536).  One extra
+keyword, `version` ('v2' default, 'v1'), selects which formulation a layer implements; `batch_A` is
+accepted in the matching reference form:
+    v2: (batch_idx[B], subset[B+B'], adj (B+B')^2)                      (vq_gnn_v2/models.py:157)
+    v1: (deg_inv[B], A_BN(r,c,v), A_BB(r,c,v)|None, A_NB_v|None, batch_idx[B])   (vq_gnn_v1/utils/dataloader.py:86)
+or as a prebuilt `graph.BatchPlan`.
+
+What differs is the execution: the per-branch Python loops (gather -> cat -> conv -> hook, ~10^4 tiny
+launches per step) become one fused CUDA launch per layer per direction over all branches, through
+libvqgnn's C-ABI.  The VQ hook keeps v1 semantics: it runs inside the layer's backward on
+(d loss / d conv-output, detached layer input) and only mutates quantiser state for the NEXT step.
+`literal_v2_hooks=True` reproduces v2's dangling-slice behaviour (the hook never fires; SURVEY.md
+Appendix B.1).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+from .convs import OurGATConv, OurGCNConv, Transformer  # noqa: F401
+from .graph import BatchPlan, CSRAdj, build_plan
+from .vq import VectorQuantizerEMA, VQBank
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------------------
+# fused message passing as an autograd Function
+# --------------------------------------------------------------------------------------------------
+_TRIGGERS = {}
+
+
+def _trigger(dev) -> Tensor:
+    t = _TRIGGERS.get(dev)
+    if t is None:
+        t = _TRIGGERS[dev] = torch.zeros((), device=dev, requires_grad=True)
+    return t
+
+
+def _mp_ws(dev) -> Tensor:
+    return torch.empty(8, dtype=torch.float64, device=dev)
+
+
+class VQConvFunction(torch.autograd.Function):
+    """Y[:B], info_backward = conv([x ; codewords], adj)  for GCN / SAGE-Mean.
+
+    forward : vqgnn_mp_fwd   (vq_gnn_v2/models.py:161-198 ; vq_gnn_v1/models.py:170-223 + mapper)
+    backward: vqgnn_mp_bwd   (adj^T dY + d info_backward / dx), then the VQ hook
+              (vq_gnn_v2/models.py:39-56 / vq_gnn_v1/models.py:71-125) via `bank.run`.
+    """
+
+    @staticmethod
+    def forward(ctx, x: Tensor, trigger: Tensor, layer: "LowRankGNNLayer", plan: BatchPlan, wu: float,
+                fire_hook: bool):
+        # `trigger` is a dummy scalar that requires grad, so backward (and with it the VQ hook) runs even
+        # when x itself needs no gradient (first layer) -- the reference gets the same effect from
+        # X_output_B.requires_grad_() (vq_gnn_v1/models.py:202).
+        _lib.require_device(x)
+        lib, st = _lib.load(), _lib.stream()
+        bank = layer.bank
+        B, C = x.shape
+        dev = x.device
+        y = torch.empty(B, C, device=dev)
+        need_info = plan.training
+        info = torch.zeros((), device=dev)
+        v1 = plan.version == 'v1'
+        gq = torch.empty(B, C, device=dev) if (v1 and plan.fwd_rval is not None) else None
+        ws = _mp_ws(dev) if need_info else None
+        _lib.check(lib.vqgnn_mp_fwd(
+            _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
+            plan.R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
+            _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, float(wu) if v1 else 1.0, float(wu),
+            _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
+            _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+        ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook = layer, plan, float(wu), fire_hook
+        ctx.save_for_backward(x, gq)
+        return y, info
+
+    @staticmethod
+    def backward(ctx, dy: Tensor, dinfo: Tensor):
+        x, gq = ctx.saved_tensors
+        layer, plan, wu = ctx.layer, ctx.plan, ctx.wu
+        lib, st = _lib.load(), _lib.stream()
+        bank = layer.bank
+        dy = dy.contiguous()
+        dinfo = dinfo.contiguous().float()
+        B, C = x.shape
+        dx = None
+        v1 = plan.version == 'v1'
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, C, device=x.device)
+            _lib.check(lib.vqgnn_mp_bwd(
+                _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val), B, _lib.ptr(dy),
+                dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
+                bank.M, bank.D, bank.Wp, 0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
+                wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0), st))
+        if ctx.fire_hook:
+            # the reference's hook(grad): vq.update(X_B, grad) ; c_indices[batch] = idx ; return grad
+            bank.run(x, dy, plan.batch_idx, True)
+        return dx, None, None, None, None, None
+
+
+def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Tensor]) -> Tensor:
+    """`conv.forward(x, adj)` of the reference on an explicit adjacency with no codeword rows."""
+    _lib.require_device(x)
+    n = x.shape[0]
+    if att_l is not None:
+        raise NotImplementedError("plain GAT propagate lands with the GAT kernels")
+    rowptr, col, val = adj.csr()
+    assert int(adj.sparse_sizes()[0]) == n
+    C = x.shape[1]
+    lib, st = _lib.load(), _lib.stream()
+    xc = x.detach().contiguous().float()
+    y = torch.empty_like(xc)
+    codes = torch.zeros(1, 1, dtype=torch.int16, device=x.device)
+    O = torch.zeros(1, 1, 8, device=x.device)
+    D = 4 if C % 4 == 0 else 1
+    _lib.check(lib.vqgnn_mp_fwd(
+        _lib.ptr(rowptr.to(torch.int32)), _lib.ptr(col.to(torch.int32)), _lib.ptr(val.float().contiguous()), None,
+        n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, 1.0, 1.0,
+        _lib.ptr(y), y.stride(0), None, 0, None, None, st))
+    return y
+
+
+# --------------------------------------------------------------------------------------------------
+# modules
+# --------------------------------------------------------------------------------------------------
+class LowRankGNNBlock(nn.Module):
+    """Per-branch state holder (vq_gnn_v2/models.py:11-63; v1 adds the per-branch conv, :42-49)."""
+
+    def __init__(self, in_channels, hidden_channels, num_M, num_D, num_N, num_branch, cluster, kmeans_iter,
+                 EMA_flag, kmeans_init, use_gcn, commitment_cost, grad_normalize_scale, hook_flag, warm_up_flag,
+                 momentum, conv_type, transformer_flag, version: str = 'v2'):
+        super().__init__()
+        self.num_M, self.num_D, self.num_N, self.EMA_flag = num_M, num_D, num_N, EMA_flag
+        self.commitment_cost, self.hook_flag = commitment_cost, hook_flag
+        self.grad_normalize_scale, self.conv_type = grad_normalize_scale, conv_type
+        self.transformer_flag, self.version = transformer_flag, version
+        if transformer_flag:
+            raise NotImplementedError("--transformer-flag is outside the hot path (SURVEY.md §2 #6)")
+        if not EMA_flag:
+            raise ValueError('Not EMA vq not studied')                     # v1/models.py:58-59
+        c = torch.randint(0, num_M, (num_N,), dtype=torch.short)           # models.py:27
+        self.register_buffer('c_indices', c)
+        add_flag = False
+        if version == 'v1':                                                # v1/models.py:42-53
+            if conv_type != 'GAT':
+                self.conv = OurGCNConv(in_channels, in_channels, normalize=False)
+            else:
+                self.conv = OurGATConv(in_channels + 1, in_channels + 1, bias=False, add_self_loops=False,
+                                       version='v1')
+            add_flag = conv_type == 'GAT'
+        self.vq = VectorQuantizerEMA(num_M, num_D, commitment_cost=commitment_cost,
+                                     grad_normalize_scale=grad_normalize_scale, warm_up_flag=warm_up_flag,
+                                     momentum=momentum, add_flag=add_flag)
+        self.kmeans_init = kmeans_init
+        self.grad_kmeans_init = kmeans_init
+        self.inited = False
+        if version == 'v1':
+            self.ln = nn.LayerNorm(in_channels, elementwise_affine=False)  # v1/models.py:65 (unused)
+
+    def init(self, X_B, batch_indices):
+        """models.py:61-63 for a single branch (the layer normally initialises all branches at once)."""
+        bank, i = self.vq.bank, self.vq._branch
+        x = X_B.detach().contiguous().float()
+        idx = bank.run(x, None, batch_indices.to(torch.int32), self.vq.training, k0=i, nbc=1, local=True)
+        return idx
+
+    def hook(self, grad):
+        raise RuntimeError("the per-branch hook is fused into LowRankGNNLayer's backward "
+                           "(VQConvFunction.backward); it is not called directly")
+
+
+class LowRankGNNLayer(nn.Module):
+    def __init__(self, in_channels, out_channels, dropout,
+                 num_M, num_D, num_N, num_branch, cluster, ln_para, no_second_fc,
+                 kmeans_iter, EMA_flag, split, kmeans_init, dropbranch, skip, use_gcn, commitment_cost,
+                 grad_normalize_scale, hook, weight_ahead, warm_up_flag, momentum, conv_type, transformer_flag,
+                 version: str = 'v2', literal_v2_hooks: bool = False):
+        super().__init__()
+        self.weight_ahead = weight_ahead
+        if self.weight_ahead:
+            if out_channels % num_D != 0:
+                raise ValueError('Cannot fully split')
+            self.num_branch = int(out_channels / num_D)
+        else:
+            if in_channels % num_D != 0:
+                raise ValueError('Cannot fully split')
+            self.num_branch = int(in_channels / num_D)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.no_second_fc, self.EMA_flag, self.split = no_second_fc, EMA_flag, split
+        self.num_D, self.num_M, self.num_N = num_D, num_M, num_N
+        self.dropbranch, self.skip = dropbranch, skip
+        self.conv_type, self.transformer_flag = conv_type, transformer_flag
+        self.version, self.literal_v2_hooks = version, literal_v2_hooks
+        self.hook_flag = hook
+        if dropbranch and dropbranch > 0:
+            raise NotImplementedError("dropbranch > 0 is unused by every reference configuration")
+        if transformer_flag:
+            raise NotImplementedError("--transformer-flag is outside the hot path (SURVEY.md §2 #6)")
+        if conv_type not in ('GCN', 'SAGE', 'GAT'):
+            raise ValueError('GNN conv type not supported')
+
+        if version == 'v2':                                               # v2/models.py:93-97
+            if conv_type != 'GAT':
+                self.conv = OurGCNConv(in_channels, in_channels, normalize=False)
+            else:
+                self.conv = OurGATConv(in_channels + 1, in_channels + 1, bias=False, add_self_loops=False)
+        self.linear_k, self.linear_v = nn.ModuleList(), nn.ModuleList()
+        self.gnn_block, self.transformer_block = nn.ModuleList(), nn.ModuleList()
+        for _ in range(self.num_branch):
+            if no_second_fc:
+                self.gnn_block.append(LowRankGNNBlock(
+                    None if version == 'v2' else num_D, None if version == 'v2' else out_channels,
+                    num_M, num_D, num_N, self.num_branch, cluster, kmeans_iter, EMA_flag, kmeans_init,
+                    use_gcn, commitment_cost, grad_normalize_scale, hook, warm_up_flag, momentum, conv_type,
+                    False, version=version))
+            else:
+                raise ValueError('second fc not studied')
+        if self.skip:
+            self.linear_skip = nn.Linear(in_channels, out_channels)
+        self.gnn_transform = nn.Linear(in_channels, out_channels)
+        self.batch_norm = nn.BatchNorm1d(out_channels, affine=False)
+        if self.conv_type == 'SAGE':
+            self.fc_sage = nn.Linear(in_channels, out_channels)
+
+        add_flag = (version == 'v1' and conv_type == 'GAT')
+        bank = VQBank(self.num_branch, num_M, num_D, grad_normalize_scale=grad_normalize_scale,
+                      warm_up_flag=warm_up_flag, momentum=momentum, add_flag=add_flag, num_N=num_N)
+        object.__setattr__(self, 'bank', bank)
+        self.sync_status = False
+        self._restack()
+
+    # ---- stacked storage <-> per-branch reference buffers -------------------------------------
+    def _restack(self):
+        """(Re)build the stacked bank from the per-branch buffers and alias them as views of it.
+        Runs after construction and after every `.to()` / `.cuda()`."""
+        blocks = list(self.gnn_block)
+        dev = blocks[0].c_indices.device
+        bank = self.bank
+        if bank.device != dev:
+            bank.to(dev)
+        for i, b in enumerate(blocks):
+            b.vq._pull_into_bank(bank, i)
+            bank.codes[:, i] = b.c_indices
+        for i, b in enumerate(blocks):
+            b.vq._owns_bank = False
+            b.vq._bind_views(bank, i)
+            b._buffers['c_indices'] = bank.codes[:, i]
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._restack()
+        return out
+
+    def _load_from_state_dict(self, *a, **k):
+        return super()._load_from_state_dict(*a, **k)   # buffers are views: copy_ writes through
+
+    # ---- reference bookkeeping ----------------------------------------------------------------
+    @property
+    def inited(self) -> bool:
+        return all(b.inited for b in self.gnn_block)
+
+    def set_inited(self, flag: bool = True):
+        for b in self.gnn_block:
+            b.inited = flag
+            b.kmeans_init = False
+            b.grad_kmeans_init = False
+
+    def check_status(self):
+        self.bank.check_status()
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, x, batch_A, warm_up_rate, unlabeled):
+        nb = self.num_branch
+        errors, X_B_norms, quantized_norms = [0] * nb, [0] * nb, [0] * nb
+        losses, info_backwards, hookeds = 0, 0, []
+        _lib.require_device(x)
+        plan = build_plan(batch_A, self.conv_type, self.num_N, self.training, x.device)
+        if plan.training != self.training:
+            raise ValueError("BatchPlan was built for a different train/eval mode")
+        x = x.float()
+        xc = x if x.is_contiguous() else x.contiguous()
+        inited = self.inited
+        do_init = (not inited or unlabeled) and (self.training or self.version == 'v2')
+        if do_init:          # models.py:165-166 (v2) / v1 models.py:164-165: feature-only warm start
+            self.bank.run(xc.detach(), None, plan.batch_idx, self.training)
+            if self.sync_status:
+                self.bank.check_status()
+        fire = (inited and self.training and not unlabeled and self.hook_flag
+                and not (self.version == 'v2' and self.literal_v2_hooks) and torch.is_grad_enabled())
+        if self.conv_type == 'GAT':
+            from .gat import gat_conv
+            y, info = gat_conv(self, xc, plan, float(warm_up_rate), fire)
+        else:
+            y, info = VQConvFunction.apply(xc, _trigger(xc.device) if fire else None, self, plan,
+                                           float(warm_up_rate), fire)
+        if self.training:
+            info_backwards = info_backwards + info                      # models.py:199-200
+        out = self.gnn_transform(y)                                     # models.py:202
+        if self.conv_type == 'SAGE':
+            out = out + self.fc_sage(x)                                 # :203-204
+        if self.skip:
+            out = out + self.linear_skip(x)                             # :228-229
+        return out, errors, X_B_norms, quantized_norms, losses, info_backwards, hookeds
+
+
+class LowRankGNN(nn.Module):
+    def __init__(self, in_channels, hidden_channels, out_channels, num_layers, dropout,
+                 num_M, num_D, num_N, num_branch=0, cluster='vq', ln_para=True, no_second_fc=False,
+                 kmeans_iter=100, EMA_flag=True, split=True, kmeans_init=False, dropbranch=0, skip=True,
+                 use_gcn=False, commitment_cost=0.5, grad_scale=(1, 1), act='relu', weight_ahead=False,
+                 bn_flag=False, warm_up_flag=False, momentum=0.1, conv_type='GCN', transformer_flag=False,
+                 alpha_dropout_flag=False, version: str = 'v2', literal_v2_hooks: bool = False):
+        super().__init__()
+        self.num_layers, self.skip, self.dropout = num_layers, skip, dropout
+        self.bn_flag, self.alpha_dropout_flag = bn_flag, alpha_dropout_flag
+        self.version, self.conv_type, self.num_N = version, conv_type, num_N
+        if self.alpha_dropout_flag:
+            self.alpha_dropout = nn.AlphaDropout(p=self.dropout)
+        self.convs, self.batch_norms = nn.ModuleList(), nn.ModuleList()
+
+        def mk(cin, cout, db):
+            return LowRankGNNLayer(cin, cout, dropout, num_M, num_D, num_N, num_branch=num_branch,
+                                   cluster=cluster, ln_para=ln_para, no_second_fc=no_second_fc,
+                                   kmeans_iter=kmeans_iter, EMA_flag=EMA_flag, split=split,
+                                   kmeans_init=kmeans_init, dropbranch=db, skip=skip, use_gcn=use_gcn,
+                                   commitment_cost=commitment_cost, grad_normalize_scale=grad_scale, hook=True,
+                                   weight_ahead=weight_ahead, warm_up_flag=warm_up_flag, momentum=momentum,
+                                   conv_type=conv_type, transformer_flag=transformer_flag, version=version,
+                                   literal_v2_hooks=literal_v2_hooks)
+        self.convs.append(mk(in_channels, hidden_channels, 0))
+        self.batch_norms.append(nn.BatchNorm1d(hidden_channels, affine=False))
+        for _ in range(num_layers - 2):
+            self.convs.append(mk(hidden_channels, hidden_channels, dropbranch))
+            self.batch_norms.append(nn.BatchNorm1d(hidden_channels, affine=False))
+        self.convs.append(mk(hidden_channels, out_channels, dropbranch))
+        self.transform = nn.Linear(out_channels, out_channels)
+        self.ln = nn.LayerNorm(hidden_channels, elementwise_affine=False)
+        if act == 'relu':
+            self.act_f = F.relu
+        elif act == 'elu':
+            self.act_f = F.elu
+        elif act == 'leaky_gelu':
+            self.act_f = lambda x: 0.1 * x + 0.9 * F.gelu(x)
+        else:
+            raise ValueError('Activation not supported!')
+
+    def prepare(self, batch_A, device=None) -> BatchPlan:
+        """Build the kernel plan once per mini-batch (shared by all layers)."""
+        device = device or next(self.parameters()).device
+        return build_plan(batch_A, self.conv_type, self.num_N, self.training, device)
+
+    def forward(self, batch, warm_up_rate=1, unlabeled=False):
+        losses_full, info_backwards_full = 0, 0
+        errors_full, X_B_norms_full, quantized_norms_full = [], [], []
+        x, batch_A = batch
+        batch_A = build_plan(batch_A, self.conv_type, self.num_N, self.training, x.device)
+        for i, conv in enumerate(self.convs[:-1]):
+            x, errors, X_B_norms, quantized_norms, losses, info_backwards, _ = \
+                conv(x, batch_A, warm_up_rate, unlabeled)
+            if self.bn_flag:
+                x = self.batch_norms[i](x)
+            x = self.act_f(x)
+            if self.alpha_dropout_flag:
+                x = self.alpha_dropout(x)
+            else:
+                x = F.dropout(x, p=self.dropout, training=self.training)
+            losses_full += losses
+            info_backwards_full += info_backwards
+            errors_full.append(errors), X_B_norms_full.append(X_B_norms)
+            quantized_norms_full.append(quantized_norms)
+        x, errors, X_B_norms, quantized_norms, losses, info_backwards, _ = \
+            self.convs[-1](x, batch_A, warm_up_rate, unlabeled)
+        losses_full += losses
+        info_backwards_full += info_backwards
+        errors_full.append(errors), X_B_norms_full.append(X_B_norms)
+        quantized_norms_full.append(quantized_norms)
+        self.errors, self.X_B_norms, self.quantized_norms = errors_full, X_B_norms_full, quantized_norms_full
+        return x, losses_full, info_backwards_full
+
+    def init(self, batch, layer_idx):
+        """Codebook warm start (models.py:370-374)."""
+        x, batch_A = batch
+        batch_A = build_plan(batch_A, self.conv_type, self.num_N, self.training, x.device)
+        for i, conv in enumerate(self.convs[:layer_idx]):
+            x, _, _, _, _, _, _ = conv(x, batch_A, 1, False)
+            x = self.act_f(x)
+
+    def set_inited(self, flag: bool = True):
+        """What main's init() does after the warm-start passes (main_node.py:30-37)."""
+        for layer in self.convs:
+            layer.set_inited(flag)
+
+    def check_status(self):
+        for layer in self.convs:
+            layer.check_status()
+
+    def inference(self, x, A):
+        raise NotImplementedError("LowRankGNN.inference is broken in the reference v2 (models.py:355) "
+                                  "and is not part of the hot path")

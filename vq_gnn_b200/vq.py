@@ -1,0 +1,327 @@
+"""`VectorQuantizerEMA` — drop-in for vq_gnn_v{1,2}/vq.py:60-279, backed by libvqgnn (sm_100a).
+
+Same constructor, method names, return shapes, buffer names and `state_dict()` keys as the reference.
+The storage is a `VQBank`: the codebooks / EMA statistics / BatchNorm running statistics of ALL
+`num_branch` quantisers of a layer stacked as `[nb, M, Wp]`, so one kernel launch covers every branch
+(the reference runs ~261 ATen ops per branch per call).  A stand-alone
+`VectorQuantizerEMA` owns a bank with nb = 1; the per-branch modules inside a `LowRankGNNLayer`
+are views into the layer's bank.
+
+Pipeline of one `update` / `feature_update`:
+    vqgnn_vq_moments  ->  [allreduce]  ->  vqgnn_vq_whiten  ->  vqgnn_vq_assign (+ per-codeword sums)
+                      ->  [allreduce]  ->  vqgnn_vq_finalize (EMA, Laplace smoothing, recovery)
+The two bracketed points are where a multi-GPU run sums its statistics over ranks (NCCL), which makes
+every rank's codebook replica identical.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+def _round4(w: int) -> int:
+    return (w + 3) // 4 * 4
+
+
+class VQBank:
+    """Stacked state of `nb` quantisers + the kernel launches.  Not an nn.Module on purpose: the
+    registered buffers live on the per-branch `VectorQuantizerEMA` modules (reference key names)
+    as views into these tensors."""
+
+    def __init__(self, nb: int, num_embeddings: int, embedding_dim: int, decay: float = 0.99,
+                 epsilon: float = 1e-24, grad_normalize_scale: Sequence[float] = (1, 1),
+                 warm_up_flag: bool = False, momentum: float = 0.1, add_flag: bool = False,
+                 num_N: int = 0):
+        self.nb, self.M, self.D = nb, num_embeddings, embedding_dim
+        self.add = 1 if add_flag else 0
+        self.Dg = embedding_dim + self.add
+        self.W = embedding_dim + self.Dg
+        self.Wp = _round4(self.W)
+        self.Ws = self.Wp + 4
+        self.decay, self.eps = decay, epsilon
+        self.scale = [float(grad_normalize_scale[0]), float(grad_normalize_scale[1])]
+        self.warm_up_flag, self.momentum = warm_up_flag, momentum
+        self.num_N = num_N
+        self.bn_inited = False
+        self.assign_impl = 0          # 0: exact fp32 SIMT, 1: tcgen05 3xTF32
+        self.process_group = None     # set (with world_size > 1) to allreduce statistics over ranks
+        self.distributed = False
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt)
+        self.E, self.O, self.Wm = z(nb, self.M, self.Wp), z(nb, self.M, self.Wp), z(nb, self.M, self.Wp)
+        self.size = z(nb, self.M)
+        self.rm_f, self.rv_f = z(nb, self.D), torch.ones(nb, self.D)
+        self.rm_g, self.rv_g = z(nb, self.Dg), torch.ones(nb, self.Dg)
+        self.nbt_f, self.nbt_g = z(nb, dt=torch.int64), z(nb, dt=torch.int64)
+        self.codes = z(max(num_N, 1), nb, dt=torch.int16)   # [N, nb]
+        self.status = z(1, dt=torch.int32)
+        self.last_idx: Optional[Tensor] = None
+
+    TENSORS = ("E", "O", "Wm", "size", "rm_f", "rv_f", "rm_g", "rv_g", "nbt_f", "nbt_g", "codes", "status")
+
+    @property
+    def device(self):
+        return self.E.device
+
+    def to(self, device):
+        for n in self.TENSORS:
+            setattr(self, n, getattr(self, n).to(device))
+        return self
+
+    # ---- the fused update ---------------------------------------------------------------------
+    def run(self, x: Tensor, g: Optional[Tensor], batch_idx: Optional[Tensor], training: bool,
+            k0: int = 0, nbc: Optional[int] = None, write_codes: bool = True,
+            local: bool = False) -> Tensor:
+        """x: [B, >= (k0+nbc)*D] (branch k reads columns k*D..), g: [B, nb*Dg] or None; with
+        `local` the operands hold only the nbc selected branches, starting at column 0.
+        Returns idx [B, nbc] int16 (codes chosen with the PRE-update codebook)."""
+        nbc = self.nb - k0 if nbc is None else nbc
+        _lib.require_device(x)
+        lib = _lib.load()
+        st = _lib.stream()
+        D, Dg, M, Wp = self.D, self.Dg, self.M, self.Wp
+        joint = g is not None
+        assert x.dtype == torch.float32 and x.stride(1) == 1
+        B = x.shape[0]
+        dev = x.device
+        c0 = 0 if local else k0
+        xk = x[:, c0 * D:(c0 + nbc) * D]
+        gk = None
+        if joint:
+            assert g.dtype == torch.float32 and g.stride(1) == 1 and g.shape[1] >= (c0 + nbc) * Dg
+            gk = g[:, c0 * Dg:(c0 + nbc) * Dg]
+        assert xk.shape[1] == nbc * D
+        C, Cg = nbc * D, (nbc * Dg if joint else 0)
+        sl = slice(k0, k0 + nbc)
+        E, O, Wm, size = self.E[sl], self.O[sl], self.Wm[sl], self.size[sl]
+        rm_f, rv_f, rm_g, rv_g = self.rm_f[sl], self.rv_f[sl], self.rm_g[sl], self.rv_g[sl]
+        nbt_f, nbt_g = self.nbt_f[sl], self.nbt_g[sl]
+        scale = torch.empty(C + Cg, device=dev)
+        shift = torch.empty(C + Cg, device=dev)
+        sums, d_count = None, None
+        count = float(B)
+        if training:
+            sums = torch.empty(2 * (C + Cg) + 1, dtype=torch.float64, device=dev)
+            _lib.check(lib.vqgnn_vq_moments(_lib.ptr(xk), xk.stride(0), _lib.ptr(gk),
+                                            gk.stride(0) if joint else 0, B, C, Cg, _lib.ptr(sums), st))
+            if self.distributed:   # global batch statistics: every rank whitens identically
+                sums[-1] = float(B)
+                torch.distributed.all_reduce(sums, group=self.process_group)
+                d_count = sums[-1:]
+        seed = 1 if (joint and training and not self.bn_inited) else 0
+        _lib.check(lib.vqgnn_vq_whiten(
+            _lib.ptr(sums), count, _lib.ptr(d_count), nbc, D, Dg, 1 if joint else 0, _lib.ptr(rm_f), _lib.ptr(rv_f),
+            _lib.ptr(rm_g) if joint else None, _lib.ptr(rv_g) if joint else None,
+            1e-5, 0.1, self.eps, self.momentum, self.scale[0], self.scale[1], 1 if training else 0, seed,
+            _lib.ptr(nbt_f) if training else None, _lib.ptr(nbt_g) if (training and joint) else None,
+            _lib.ptr(scale), _lib.ptr(shift), st))
+        if joint and training:
+            self.bn_inited = True
+        idx = torch.empty(B, nbc, dtype=torch.int16, device=dev)
+        stats = None
+        if training:
+            stats = torch.empty(nbc, M, self.Ws, device=dev)
+            _lib.check(lib.vqgnn_fill_zero(_lib.ptr(stats), stats.numel() * 4, st))
+        codes_ptr, bidx = None, None
+        if write_codes and batch_idx is not None:
+            assert batch_idx.dtype == torch.int32 and batch_idx.is_cuda
+            bidx = batch_idx
+            codes_ptr = _lib.C.c_void_p(self.codes.data_ptr() + 2 * k0)
+        _lib.check(lib.vqgnn_vq_assign(
+            _lib.ptr(xk), xk.stride(0), _lib.ptr(gk), gk.stride(0) if joint else 0, _lib.ptr(scale),
+            _lib.ptr(shift), _lib.ptr(E), B, nbc, M, D, Dg, Wp, _lib.ptr(bidx), codes_ptr, self.nb,
+            _lib.ptr(idx), _lib.ptr(stats), self.assign_impl, st))
+        if training:
+            if self.distributed:
+                torch.distributed.all_reduce(stats, group=self.process_group)
+            _lib.check(lib.vqgnn_vq_finalize(
+                _lib.ptr(stats), nbc, M, D, Dg, Wp, 1 if joint else 0, float(self.decay),
+                1 if self.warm_up_flag else 0, self.eps, self.scale[0], self.scale[1], _lib.ptr(rm_f),
+                _lib.ptr(rv_f), _lib.ptr(rm_g) if joint else None, _lib.ptr(rv_g) if joint else None,
+                _lib.ptr(size), _lib.ptr(Wm), _lib.ptr(E), _lib.ptr(O), _lib.ptr(self.status), st))
+        self.last_idx = idx
+        self.last_stats = stats
+        return idx
+
+    def check_status(self):
+        """Lazy 'Bad Init!' check (vq.py:188-189, 253-254): one host sync."""
+        if self.status.is_cuda and int(self.status.item()) & 1:
+            self.status.zero_()
+            raise ValueError('Bad Init!')
+
+
+class VectorQuantizerEMA(nn.Module):
+    """Reference signature: vq_gnn_v2/vq.py:61-62."""
+
+    def __init__(self, num_embeddings, embedding_dim, commitment_cost=0.5, decay=0.99, epsilon=1e-24,
+                 grad_normalize_scale=(1, 1), warm_up_flag=False, momentum=0.1, add_flag=False,
+                 _bank: Optional[VQBank] = None, _branch: int = 0):
+        super().__init__()
+        if type(grad_normalize_scale) is not list:
+            raise ValueError('grad scale type wrong!')          # vq.py:91-92
+        self.add_flag = add_flag
+        added_dim = 1 if add_flag else 0
+        self._embedding_dim, self._num_embeddings = embedding_dim, num_embeddings
+        self._commitment_cost, self._warm_up_flag = commitment_cost, warm_up_flag
+        self._decay, self._epsilon = decay, epsilon
+        self.grad_normalize_scale = grad_normalize_scale
+        D, W = embedding_dim, embedding_dim * 2 + added_dim
+        # same RNG consumption as the reference constructor (vq.py:73-80)
+        emb = torch.randn(num_embeddings, W)
+        ema_w = torch.zeros(num_embeddings, W)
+        if warm_up_flag:
+            ema_w.normal_()
+        emb[:, D:2 * D] *= grad_normalize_scale[0]
+        ema_w[:, D:2 * D] *= grad_normalize_scale[0]
+        if add_flag:
+            emb[:, 2 * D] *= grad_normalize_scale[1]
+            ema_w[:, 2 * D] *= grad_normalize_scale[1]
+        self.register_buffer('_embedding', emb)
+        self.register_buffer('_embedding_output', torch.zeros(num_embeddings, W))
+        self.register_buffer('_ema_cluster_size', torch.zeros(num_embeddings))
+        self.register_buffer('_ema_w', ema_w)
+        self.batch_norm_feat = nn.BatchNorm1d(embedding_dim, affine=False)
+        self.batch_norm_grad = nn.BatchNorm1d(embedding_dim + added_dim, eps=epsilon, affine=False,
+                                              momentum=momentum)
+        self._owns_bank = _bank is None
+        self._branch = _branch
+        self.lazy_status = False
+        if _bank is None:
+            _bank = VQBank(1, num_embeddings, embedding_dim, decay, epsilon, grad_normalize_scale,
+                           warm_up_flag, momentum, add_flag)
+        object.__setattr__(self, '_bank', _bank)   # not a submodule / buffer
+        if self._owns_bank:
+            self._rebind()
+
+    # ---- storage plumbing -------------------------------------------------------------------
+    @property
+    def bank(self) -> VQBank:
+        return self._bank
+
+    @property
+    def bn_inited(self) -> bool:
+        return self._bank.bn_inited
+
+    @bn_inited.setter
+    def bn_inited(self, v: bool):
+        self._bank.bn_inited = bool(v)
+
+    def _pull_into_bank(self, bank: VQBank, i: int):
+        """Copy this module's (possibly just-moved / just-loaded) buffers into slot i of `bank`."""
+        W = bank.W
+        bank.E[i, :, :W] = self._embedding
+        bank.O[i, :, :W] = self._embedding_output
+        bank.Wm[i, :, :W] = self._ema_w
+        bank.size[i] = self._ema_cluster_size
+        bank.rm_f[i], bank.rv_f[i] = self.batch_norm_feat.running_mean, self.batch_norm_feat.running_var
+        bank.rm_g[i], bank.rv_g[i] = self.batch_norm_grad.running_mean, self.batch_norm_grad.running_var
+        bank.nbt_f[i] = self.batch_norm_feat.num_batches_tracked
+        bank.nbt_g[i] = self.batch_norm_grad.num_batches_tracked
+
+    def _bind_views(self, bank: VQBank, i: int):
+        """Re-point the registered buffers at views of slot i of `bank`."""
+        W = bank.W
+        object.__setattr__(self, '_bank', bank)
+        self._branch = i
+        self._buffers['_embedding'] = bank.E[i, :, :W]
+        self._buffers['_embedding_output'] = bank.O[i, :, :W]
+        self._buffers['_ema_w'] = bank.Wm[i, :, :W]
+        self._buffers['_ema_cluster_size'] = bank.size[i]
+        bf, bg = self.batch_norm_feat, self.batch_norm_grad
+        bf._buffers['running_mean'], bf._buffers['running_var'] = bank.rm_f[i], bank.rv_f[i]
+        bg._buffers['running_mean'], bg._buffers['running_var'] = bank.rm_g[i], bank.rv_g[i]
+        bf._buffers['num_batches_tracked'] = bank.nbt_f[i]
+        bg._buffers['num_batches_tracked'] = bank.nbt_g[i]
+
+    def _rebind(self):
+        dev = self._embedding.device
+        bank = self._bank
+        if bank.device != dev:
+            bank.to(dev)
+        self._pull_into_bank(bank, 0)
+        self._bind_views(bank, 0)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if self._owns_bank:
+            self._rebind()
+        return out
+
+    # ---- reference API ----------------------------------------------------------------------
+    def feature_kmeans_init(self, kmeans_centroids, kmeans_counts):   # vq.py:102-105
+        D = self._embedding_dim
+        self._embedding[:, :D] = kmeans_centroids
+        self._ema_cluster_size.copy_(kmeans_counts)
+        self._ema_w[:, :D] = kmeans_centroids * kmeans_counts.unsqueeze(1)
+
+    def kmeans_init(self, kmeans_centroids, kmeans_counts):           # vq.py:108-118
+        D = self._embedding_dim
+        self._embedding.copy_(kmeans_centroids)
+        self._ema_cluster_size.copy_(kmeans_counts)
+        self._ema_w.copy_(kmeans_centroids * kmeans_counts.unsqueeze(1))
+        self._embedding[:, D:2 * D] *= self.grad_normalize_scale[0]
+        self._ema_w[:, D:2 * D] *= self.grad_normalize_scale[0]
+        if self.add_flag:
+            self._embedding[:, 2 * D] *= self.grad_normalize_scale[1]
+            self._ema_w[:, 2 * D] *= self.grad_normalize_scale[1]
+
+    def get(self):                 # vq.py:120
+        return self._embedding_output
+
+    def get_codebook(self):        # vq.py:123
+        return self._embedding_output[:, :self._embedding_dim]
+
+    def get_grad(self):            # vq.py:126
+        return self._embedding_output[:, self._embedding_dim:]
+
+    def get_feat_cen_norm(self):
+        return torch.norm(torch.mean(self._embedding[:, :self._embedding_dim], dim=0)).item()
+
+    def get_grad_cen_norm(self):
+        return torch.norm(torch.mean(self._embedding[:, self._embedding_dim:], dim=0)).item()
+
+    def _get_feat_embed(self):
+        return self._embedding[:, :self._embedding_dim]
+
+    def feature_update(self, X_B: Tensor) -> Tensor:
+        """vq.py:160-202.  Returns encoding_indices [B, 1] int64."""
+        x = X_B.detach().contiguous().float()
+        idx = self._bank.run(x, None, None, self.training, k0=self._branch, nbc=1, write_codes=False,
+                             local=True)
+        if self.training and not self.lazy_status:
+            self._bank.check_status()
+        return idx.to(torch.long)
+
+    def update(self, X_B: Tensor, grad: Tensor):
+        """vq.py:204-279.  Returns (encoding_indices [B,1] int64, encodings).  `encodings` (the dense
+        one-hot [B, M] no caller uses) is built lazily: a `LazyOneHot` whose
+        `.dense()` materialises it."""
+        x = X_B.detach().contiguous().float()
+        g = grad.detach().contiguous().float()
+        bank, i = self._bank, self._branch
+        idx = bank.run(x, g, None, self.training, k0=i, nbc=1, write_codes=False, local=True)
+        if self.training and not self.lazy_status:
+            bank.check_status()
+        idx = idx.to(torch.long)
+        return idx, LazyOneHot(idx, self._num_embeddings)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("the reference VectorQuantizerEMA defines no forward()")
+
+
+class LazyOneHot:
+    def __init__(self, idx: Tensor, M: int):
+        self.idx, self.M = idx, M
+
+    def dense(self) -> Tensor:
+        out = torch.zeros(self.idx.shape[0], self.M, device=self.idx.device)
+        return out.scatter_(1, self.idx, 1)
+
+    def sum(self, dim=0):
+        assert dim == 0
+        return torch.bincount(self.idx.view(-1), minlength=self.M).float()
