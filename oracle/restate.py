@@ -331,8 +331,10 @@ class OracleLayer:
             y = gcn_propagate(adj, xin)
         y_B = y[:B]
         if self.inited and self.training and not unlabeled and self.hook_mode == 'fire' \
-                and y_B.requires_grad:
+                and torch.is_grad_enabled():
             X_det = x.detach()
+            if not y_B.requires_grad:      # x_output_B.requires_grad_() on a no-grad tensor: a new leaf
+                y_B = y_B.detach().requires_grad_()
 
             def hook(grad, X_det=X_det, batch_idx=batch_idx):
                 for i in range(self.nb):
@@ -364,7 +366,10 @@ class OracleLayer:
             else:
                 X_out = gcn_propagate(adj, X_in)
             X_out_B, X_out_M = X_out[:B], X_out[B:]                    # :197
-            if self.inited and self.training and not unlabeled and X_out_B.requires_grad:   # :199-203
+            if self.inited and self.training and not unlabeled and torch.is_grad_enabled():  # :199-203
+                if not X_out_B.requires_grad:   # X_output_B.requires_grad_() (:202) makes it a leaf
+                    X_out_B = X_out_B.detach().requires_grad_()
+
                 def hook(grad, i=i, X_det=X_B.detach(), batch_idx=batch_idx):
                     self._fire(i, X_det, batch_idx, grad)
                     return grad

@@ -51,3 +51,29 @@ def to_shim_batch(batch_A, ts):
 def rel_err(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def loss_weights(shape):
+    """Per-element random loss weights: the gradient must VARY across batch rows, otherwise the
+    gradient BatchNorm (eps = 1e-24, vq.py:87) divides rounding noise by 1e-12."""
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(77))
+
+
+def state_mismatches(sd_cuda, sd_oracle, tol):
+    """Compare reference-keyed state dicts.  Running means are compared on the scale of the matching
+    running std (a gradient that went through a BatchNorm has an exactly-zero batch mean, so its
+    running mean is pure rounding noise).  Returns (list of failing keys, number of differing codes)."""
+    bad, n_codes = [], 0
+    for k, v in sd_oracle.items():
+        c = sd_cuda[k].detach().cpu()
+        if not v.is_floating_point():
+            n_codes += int((c != v).sum())
+            continue
+        if k.endswith("running_mean"):
+            std = sd_oracle[k[:-len("running_mean")] + "running_var"].double().sqrt()
+            err = float(((c.double() - v.double()).abs() / (std + v.double().abs() + 1e-30)).max())
+        else:
+            err = rel_err(c, v)
+        if not err < tol:
+            bad.append((k, err))
+    return bad, n_codes

@@ -1,0 +1,178 @@
+"""GPU parity: LowRankGNNLayer / LowRankGNN fwd + bwd + VQ hook (CUDA through the C-ABI) vs the CPU
+oracle (oracle/restate.py, itself pinned to the unmodified reference) on identical state and inputs."""
+import pytest
+import torch
+
+import vq_gnn_b200 as V
+from oracle import restate
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+def _run_cuda(layer, batch_A, x, steps, dev, wu=1.0):
+    layer.train()
+    outs = []
+    bA = H.batch_to(batch_A, dev)
+    for s in range(steps):
+        if s == 1:
+            layer.set_inited(True)
+        xx = x.clone().to(dev).requires_grad_(True)
+        for p in layer.parameters():
+            p.grad = None
+        out = layer(xx, bA, wu, False)
+        w = H.loss_weights(out[0].shape).to(dev)
+        loss = (out[0] * w).sum() + out[5]
+        loss.backward()
+        outs.append((out[0].detach().cpu(), torch.as_tensor(out[5]).detach().cpu(), xx.grad.cpu(),
+                     {k: p.grad.cpu() for k, p in layer.named_parameters() if p.grad is not None}))
+    return outs
+
+
+def _run_oracle(o, batch_A, x, steps, wu=1.0):
+    o.train()
+    outs = []
+    for s in range(steps):
+        if s == 1:
+            o.set_inited(True)
+        xx = x.clone().requires_grad_(True)
+        for p in o.params.values():
+            p.grad = None
+        out, info = o(xx, batch_A, wu, False)
+        loss = (out * H.loss_weights(out.shape)).sum() + info
+        loss.backward()
+        outs.append((out.detach(), torch.as_tensor(info).detach(), xx.grad.clone(),
+                     {k: p.grad.clone() for k, p in o.params.items() if p.grad is not None}))
+    return outs
+
+
+def _compare(c_outs, o_outs, layer, o):
+    for s, ((co, ci, cg, cp), (oo, oi, og, op)) in enumerate(zip(c_outs, o_outs)):
+        assert H.rel_err(co, oo) < REL_TOL, (s, "out", H.rel_err(co, oo))
+        assert abs(float(ci) - float(oi)) <= REL_TOL * max(1e-3, abs(float(oi))), (s, "info", float(ci), float(oi))
+        assert H.rel_err(cg, og) < REL_TOL, (s, "dx", H.rel_err(cg, og))
+        for k in op:
+            if k in cp:
+                assert H.rel_err(cp[k], op[k]) < REL_TOL, (s, k)
+    bad, n_code_mismatch = H.state_mismatches(layer.state_dict(), o.state_dict(), REL_TOL)
+    assert not bad, bad
+    assert n_code_mismatch == 0, n_code_mismatch
+
+
+CASES = [("v2", "GCN", 8, 4, False), ("v2", "SAGE", 8, 4, False), ("v1", "GCN", 8, 4, False),
+         ("v1", "SAGE", 8, 4, False), ("v2", "GCN", 128, 4, True), ("v1", "SAGE", 128, 4, False),
+         ("v2", "SAGE", 12, 2, False), ("v1", "GCN", 24, 8, True), ("v2", "GCN", 52, 4, False)]
+
+
+@pytest.mark.parametrize("version,conv,C,D,skip", CASES)
+def test_layer_matches_oracle(version, conv, C, D, skip):
+    dev = torch.device("cuda:0")
+    N, B, M, C_out = 400, 120, 16, 10
+    g = H.make_graph(N, 2000, conv, version, seed=7)
+    batch_A = H.make_batch(g, B, version, seed=7)
+    torch.manual_seed(11)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, C_out, M, D, N, conv, skip=skip), version=version)
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, C_out, M, D, N, conv, version, skip=skip, warm_up_flag=True).load_state_dict(sd)
+    layer = layer.to(dev)
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    c_outs = _run_cuda(layer, batch_A, x, 4, dev, wu=0.7)
+    o_outs = _run_oracle(o, batch_A, x, 4, wu=0.7)
+    _compare(c_outs, o_outs, layer, o)
+    layer.check_status()
+    # the hook really fired: gradient codewords became non-zero, info_backward is non-zero
+    assert float(layer.bank.O[:, :, D:2 * D].abs().sum()) > 0
+    assert abs(float(c_outs[-1][1])) > 0
+
+
+def test_literal_v2_hooks_never_fire():
+    dev = torch.device("cuda:0")
+    N, B, M, C = 300, 80, 16, 8
+    g = H.make_graph(N, 1200, "GCN", "v2", seed=2)
+    batch_A = H.make_batch(g, B, "v2", seed=2)
+    torch.manual_seed(1)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, 6, M, 4, N, "GCN"), version="v2", literal_v2_hooks=True)
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, 6, M, 4, N, "GCN", "v2", warm_up_flag=True, hook_mode="literal_v2").load_state_dict(sd)
+    layer = layer.to(dev)
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    _compare(_run_cuda(layer, batch_A, x, 3, dev), _run_oracle(o, batch_A, x, 3), layer, o)
+    assert float(layer.bank.O[:, :, 4:].abs().sum()) == 0
+
+
+def test_eval_mode_and_unlabeled():
+    dev = torch.device("cuda:0")
+    N, B, M, C = 300, 80, 16, 8
+    for version, conv in (("v2", "GCN"), ("v1", "SAGE")):
+        g = H.make_graph(N, 1200, conv, version, seed=4)
+        torch.manual_seed(2)
+        layer = V.LowRankGNNLayer(*H.layer_args(C, 6, M, 4, N, conv), version=version)
+        sd = {k: v.clone() for k, v in layer.state_dict().items()}
+        o = restate.OracleLayer(C, 6, M, 4, N, conv, version, warm_up_flag=True).load_state_dict(sd)
+        layer = layer.to(dev)
+        x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+        tr = H.make_batch(g, B, version, seed=4, train=True)
+        _compare(_run_cuda(layer, tr, x, 2, dev), _run_oracle(o, tr, x, 2), layer, o)
+        ev = H.make_batch(g, B, version, seed=5, train=False)
+        layer.eval(), o.train(False)
+        with torch.no_grad():
+            out_c = layer(x.to(dev), H.batch_to(ev, dev), 1, False)
+            out_o, info_o = o(x, ev, 1.0, False)
+        assert H.rel_err(out_c[0], out_o) < REL_TOL
+        assert out_c[5] == 0 and info_o == 0
+
+
+def test_full_model_train_step_matches_oracle_stack():
+    """3-layer LowRankGNN (bn + leaky_gelu) vs the same stack built from OracleLayers."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    N, B, M, D = 500, 150, 16, 4
+    for version, conv in (("v2", "GCN"), ("v1", "SAGE")):
+        g = H.make_graph(N, 2500, conv, version, seed=9)
+        batch_A = H.make_batch(g, B, version, seed=9)
+        torch.manual_seed(5)
+        model = V.LowRankGNN(12, 16, 7, 3, 0., M, D, N, no_second_fc=True, skip=False, commitment_cost=0.,
+                             grad_scale=[1, 1], act='leaky_gelu', bn_flag=True, warm_up_flag=True,
+                             conv_type=conv, version=version)
+        dims = [(12, 16), (16, 16), (16, 7)]
+        oracles = []
+        for li, (ci, co) in enumerate(dims):
+            lsd = {k[len(f"convs.{li}."):]: v.clone() for k, v in model.state_dict().items()
+                   if k.startswith(f"convs.{li}.")}
+            oracles.append(restate.OracleLayer(ci, co, M, D, N, conv, version, warm_up_flag=True).load_state_dict(lsd))
+        model = model.to(dev).train()
+        x = torch.randn(B, 12, generator=torch.Generator().manual_seed(3))
+        y = torch.randint(0, 7, (B,), generator=torch.Generator().manual_seed(4))
+        bA = H.batch_to(batch_A, dev)
+        for step in range(4):
+            if step == 1:
+                model.set_inited(True)
+                for o in oracles:
+                    o.set_inited(True)
+            # --- CUDA
+            model.zero_grad()
+            out, _, info = model((x.to(dev), bA), 1)
+            loss = F.cross_entropy(out, y.to(dev)) + info
+            loss.backward()
+            # --- oracle stack (vq_gnn_v2/models.py:308-348)
+            h = x.clone()
+            info_o = 0
+            for li, o in enumerate(oracles):
+                for p in o.params.values():
+                    p.grad = None
+                h, inf = o(h, batch_A, 1.0, False)
+                info_o = info_o + inf
+                if li < 2:
+                    h = F.batch_norm(h, None, None, training=True)
+                    h = restate.act_leaky_gelu(h)
+            loss_o = F.cross_entropy(h, y) + info_o
+            loss_o.backward()
+            assert H.rel_err(out, h) < 5 * REL_TOL, (version, step, H.rel_err(out, h))
+            assert abs(float(loss) - float(loss_o)) < 5 * REL_TOL * max(1.0, abs(float(loss_o)))
+            for li, o in enumerate(oracles):
+                gw = model.convs[li].gnn_transform.weight.grad.cpu()
+                assert H.rel_err(gw, o.params["gnn_transform.weight"].grad) < 5 * REL_TOL, (version, step, li)
+        for li, o in enumerate(oracles):
+            bad, n_codes = H.state_mismatches(model.convs[li].state_dict(), o.state_dict(), 5 * REL_TOL)
+            assert not bad and n_codes == 0, (version, li, bad, n_codes)

@@ -42,7 +42,7 @@ def test_vq_matches_reference(M, D, B, add_flag, warm):
         assert torch.allclose(sd[k], v, rtol=1e-6, atol=1e-7), k
 
 
-def _run_ref_layer(ref, version, conv, sd, args, batch_A, x, steps, ts):
+def _run_ref_layer(ref, version, conv, sd, args, batch_A, x, steps, ts, x_grad=True):
     layer = ref.models.LowRankGNNLayer(*args)
     layer.load_state_dict(sd)
     layer.train()
@@ -52,18 +52,19 @@ def _run_ref_layer(ref, version, conv, sd, args, batch_A, x, steps, ts):
         if s == 1:
             for b in layer.gnn_block:
                 b.inited = True
-        xx = x.clone().requires_grad_(True)
+        xx = x.clone().requires_grad_(x_grad)
         for p in layer.parameters():
             p.grad = None
         out = layer(xx, bA, 1, False)
-        loss = (out[0] * torch.linspace(-1, 1, out[0].shape[1])).sum() + out[5]
+        loss = (out[0] * H.loss_weights(out[0].shape)).sum() + out[5]
         loss.backward()
-        outs.append((out[0].detach(), torch.as_tensor(out[5]).detach(), xx.grad.clone(),
+        outs.append((out[0].detach(), torch.as_tensor(out[5]).detach(),
+                     xx.grad.clone() if x_grad else torch.zeros(1),
                      {k: p.grad.clone() for k, p in layer.named_parameters() if p.grad is not None}))
     return outs, layer.state_dict()
 
 
-def _run_oracle_layer(version, conv, sd, cfg, batch_A, x, steps, hook_mode):
+def _run_oracle_layer(version, conv, sd, cfg, batch_A, x, steps, hook_mode, x_grad=True):
     o = restate.OracleLayer(cfg["C"], cfg["C_out"], cfg["M"], cfg["D"], cfg["N"], conv, version, skip=cfg["skip"],
                             warm_up_flag=True, hook_mode=hook_mode).load_state_dict(sd)
     o.train()
@@ -71,20 +72,22 @@ def _run_oracle_layer(version, conv, sd, cfg, batch_A, x, steps, hook_mode):
     for s in range(steps):
         if s == 1:
             o.set_inited(True)
-        xx = x.clone().requires_grad_(True)
+        xx = x.clone().requires_grad_(x_grad)
         for p in o.params.values():
             p.grad = None
         out, info = o(xx, batch_A, 1.0, False)
-        loss = (out * torch.linspace(-1, 1, out.shape[1])).sum() + info
+        loss = (out * H.loss_weights(out.shape)).sum() + info
         loss.backward()
-        outs.append((out.detach(), torch.as_tensor(info).detach(), xx.grad.clone(),
+        outs.append((out.detach(), torch.as_tensor(info).detach(),
+                     xx.grad.clone() if x_grad else torch.zeros(1),
                      {k: p.grad.clone() for k, p in o.params.items() if p.grad is not None}))
     return outs, o.state_dict()
 
 
+@pytest.mark.parametrize("x_grad", [True, False])
 @pytest.mark.parametrize("version,conv", [("v2", "GCN"), ("v2", "SAGE"), ("v2", "GAT"), ("v1", "GCN"),
                                           ("v1", "SAGE"), ("v1", "GAT")])
-def test_layer_matches_reference(version, conv):
+def test_layer_matches_reference(version, conv, x_grad):
     ref = ref_loader.load_reference(version)
     ts = ref_loader.shim_sparse()
     cfg = dict(N=300, B=80, C=8, C_out=6, M=16, D=4, skip=(conv == "GAT"))
@@ -95,10 +98,10 @@ def test_layer_matches_reference(version, conv):
     sd = ref.models.LowRankGNNLayer(*args).state_dict()
     x = torch.randn(cfg["B"], cfg["C"], generator=torch.Generator().manual_seed(3))
     steps = 4
-    r_outs, r_sd = _run_ref_layer(ref, version, conv, sd, args, batch_A, x, steps, ts)
+    r_outs, r_sd = _run_ref_layer(ref, version, conv, sd, args, batch_A, x, steps, ts, x_grad)
     # the live v2 reference never fires its hook (dangling slice)
     o_outs, o_sd = _run_oracle_layer(version, conv, sd, cfg, batch_A, x, steps,
-                                     "literal_v2" if version == "v2" else "fire")
+                                     "literal_v2" if version == "v2" else "fire", x_grad)
     for s, ((ro, ri, rg, rp), (oo, oi, og, op)) in enumerate(zip(r_outs, o_outs)):
         assert H.rel_err(oo, ro) < 2e-5, (s, "out")
         assert abs(float(oi) - float(ri)) <= 2e-5 * max(1.0, abs(float(ri))), (s, "info", float(oi), float(ri))
