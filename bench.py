@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py — train nodes/sec per VQ-GNN layer on B200 (BASELINE.json metric).
+
+Workload at N=1 (configs[1]): VQ-GNN SAGE-Mean on a synthetic Reddit-shaped graph (232,965 nodes,
+~114.6M directed edges, 602-d padded to 604, 41 classes), hidden 128, num-M 1024, num-D 4, batch 6000,
+cont sampler walk 3, v1 formulation, --warm-up --bn-flag --recovery-flag (README.md:79-82).
+One "step" = one pass of the hot path over one batch: 3-layer LowRankGNN forward + loss + backward
+(the VQ assignment + EMA update of every layer fire inside backward) + RMSprop step.
+value = B * num_layers / t_step   [batch nodes / second / layer].
+
+N > 1: each rank owns a contiguous node partition and its own batch; codebook statistics
+(per-codeword sums/counts + whitening moments) and dense weight gradients are allreduced with NCCL
+each step (weak scaling: per-GPU batch fixed).
+
+Keys: see the task contract.  `roofline` is for the dominant kernel of the step (found live with CUDA
+events around every C-ABI launch), `cpu_baseline` times the oracle port (oracle/restate.py) on the
+host cores on a bounded sample, `e2e` runs the same step from pinned HOST buffers through the public
+API (H2D copies + plan construction inside the timed region, loss read back).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(name="c2_reddit_sage_v1", N=232_965, E=57_307_946, feat=602, C_in=604, hidden=128, classes=41,
+           M=1024, D=4, B=6000, walk=3, layers=3, conv="SAGE", version="v1", power_law=2.2)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            try:
+                sm.append(float(f[0])), (mx := float(f[1]))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        # median over the busier half of the samples (under load)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction (synthetic, seeded; generated on the GPU with torch ops -- not timed)
+# ------------------------------------------------------------------------------------------------
+def build_workload(dev, rank: int, world: int, scale: float = 1.0, n_batches: int = 4):
+    from vq_gnn_b200 import sampling, synth
+    c = CFG
+    N, E = int(c["N"] * scale), int(c["E"] * scale)
+    t0 = time.time()
+    rowptr, row, col = synth.random_edges(N, E, seed=0, power_law=c["power_law"], device=dev)
+    g = synth.normalized_graph(N, rowptr, row, col, c["conv"], c["version"])
+    del row
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    # rank r samples its seeds from its own contiguous node partition
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    seeds = lo + torch.randperm(hi - lo, generator=gen, device=dev)[:c["B"]]
+    node_lists = sampling.cont_sampler(g, seeds, c["walk"], c["B"], generator=gen)[:n_batches]
+    batches = []
+    for nodes in node_lists:
+        x = torch.randn(nodes.numel(), c["C_in"], generator=gen, device=dev)
+        x[:, c["feat"]:] = 0          # zero padding to a multiple of num_D (v2/utils/misc.py:212-219)
+        y = torch.randint(0, c["classes"], (nodes.numel(),), generator=gen, device=dev)
+        batches.append((x, sampling.collate_batch_v1(g, nodes, True, True), y))
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    nnz_bn = [int(b[1][1][0].numel()) for b in batches]
+    nnz_bb = [int(b[1][2][0].numel()) for b in batches]
+    log(f"[bench] graph N={N} nnz={g.nnz} built in {time.time() - t0:.1f}s; batches B={[b[0].shape[0] for b in batches]} "
+        f"nnz(A_BN)={nnz_bn} nnz(A_BB)={nnz_bb}")
+    return g, batches
+
+
+def build_model(dev, N, distributed: bool, assign_impl: int = 0):
+    import vq_gnn_b200 as V
+    c = CFG
+    torch.manual_seed(0)
+    model = V.LowRankGNN(c["C_in"], c["hidden"], c["classes"], c["layers"], 0.0, c["M"], c["D"], N,
+                         no_second_fc=True, skip=False, commitment_cost=0.0, grad_scale=[1, 1], act="leaky_gelu",
+                         bn_flag=True, warm_up_flag=True, momentum=0.1, conv_type=c["conv"], version=c["version"])
+    model = model.to(dev).train()
+    for layer in model.convs:
+        layer.bank.assign_impl = assign_impl
+        layer.bank.distributed = distributed
+    return model
+
+
+def warm_start(model, batches):
+    """The reference's init(): layer-wise feature-only codebook warm start (v1/main_node.py init())."""
+    with torch.no_grad():
+        for layer_idx in range(1, model.num_layers + 1):
+            for x, bA, _ in batches:
+                model.init((x, bA), layer_idx)
+    model.set_inited(True)
+    model.check_status()
+
+
+def train_step(model, opt, x, batch_A, y, distributed: bool):
+    opt.zero_grad(set_to_none=True)
+    out, _, info = model((x, batch_A), 1)
+    loss = F.cross_entropy(out, y) + info
+    loss.backward()
+    if distributed:
+        grads = [p.grad for p in model.parameters() if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        torch.distributed.all_reduce(flat)
+        flat /= torch.distributed.get_world_size()
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+    opt.step()
+    return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work per launch, used for the roofline of the dominant kernel
+# ------------------------------------------------------------------------------------------------
+def algorithmic_work(kernel: str, plan, C: int, nb: int, M: int, B: int):
+    nnz = plan.nnz
+    nnz_t = int(plan.bwd_col.numel())
+    tail = int((plan.fwd_col >= B).sum())
+    if kernel == "vqgnn_mp_fwd":    # v1 form: nnz(A_BN)*(8 + 4 rval + nb*2 codes) + in-batch*8 + x r + y,gq w + codebook
+        by = tail * (12 + nb * 2) + (nnz - tail) * 8 + (B + 1) * 4 + 3 * B * C * 4 + M * C * 2 * 4
+        return by, "hbm"
+    if kernel == "vqgnn_mp_bwd":
+        by = nnz_t * 8 + (B + 1) * 4 + 3 * B * C * 4
+        return by, "hbm"
+    if kernel == "vqgnn_vq_assign":  # joint: FLOPs = 2*B*M*2C
+        return 4.0 * B * M * C, "tensor"
+    if kernel == "vqgnn_vq_moments":
+        return 2 * B * C * 4, "hbm"
+    if kernel == "vqgnn_vq_finalize":
+        return nb * M * (12 * 4 + 8 * 4 * 4 + 4 * 2), "hbm"
+    return 0, "hbm"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(batches_cpu, n_branches: int, steps: int, warmup: int, N: int):
+    """Times oracle/restate.py (the CPU restatement of the reference; the Python reference itself cannot
+    travel to the GPU box).  Sample: `n_branches` of the 32 branches of ONE hidden layer (C=128) of the
+    config-2 batch, fwd + bwd + VQ update, scaled to the full layer."""
+    from oracle import restate
+    c = CFG
+    torch.set_num_threads(os.cpu_count())
+    x_full, bA, _ = batches_cpu[0]
+    B = x_full.shape[0]
+    C = c["hidden"]
+    nb = C // c["D"]
+    torch.manual_seed(0)
+    layer = restate.OracleLayer(C, C, c["M"], c["D"], N, c["conv"], c["version"], warm_up_flag=True,
+                                sparse=True, branches=list(range(n_branches)))
+    layer.params = {"gnn_transform.weight": (torch.randn(C, C) * 0.05).requires_grad_(True),
+                    "gnn_transform.bias": torch.zeros(C, requires_grad=True),
+                    "fc_sage.weight": (torch.randn(C, C) * 0.05).requires_grad_(True),
+                    "fc_sage.bias": torch.zeros(C, requires_grad=True)}
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(1))
+    w = torch.randn(B, C, generator=torch.Generator().manual_seed(2))
+    layer.train()
+    times = []
+    for s in range(warmup + steps):
+        if s == 1:
+            layer.set_inited(True)
+        xx = x.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        out, info = layer(xx, bA, 1.0, False)
+        ((out * w).sum() + info).backward()
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    t_layer = (sum(times) / len(times)) * (nb / n_branches)
+    return B / t_layer, t_layer, B
+
+
+def batch_to_cpu(batch):
+    x, bA, y = batch
+    mv = lambda t: None if t is None else (tuple(u.cpu() for u in t) if isinstance(t, tuple) else t.cpu())
+    return x.cpu(), tuple(mv(t) for t in bA), y.cpu()
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
+    ap.add_argument("--assign-impl", type=int, default=int(os.environ.get("VQGNN_ASSIGN_IMPL", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-branches", type=int, default=4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    c = CFG
+    config = {"workload": "configs[1]: VQ-GNN SAGE-Mean (v1 formulation), synthetic Reddit-shaped graph "
+                          f"N={c['N']}, ~{2 * c['E'] / 1e6:.1f}M directed edges, 602-d (padded 604), hidden 128, "
+                          "num-M 1024, num-D 4, batch 6000, cont sampler walk 3, 3 layers (604->128->128->41)",
+              "step": "3-layer fwd + CE loss + bwd (VQ assign + EMA update of every layer inside bwd) + RMSprop",
+              "value_formula": "B * num_layers / t_step", "batch_nodes": c["B"], "num_layers": c["layers"],
+              "parallelism": f"dp{world} (node-partitioned batches; EMA stats + weight grads allreduced)",
+              "l2": "4 distinct batches rotated AND a 256 MiB L2 flush between timed steps"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dev = torch.device("cuda:0") if torch.cuda.is_available() else torch.device("cpu")
+        g, batches = build_workload(dev, 0, 1, args.scale, n_batches=1)
+        batches_cpu = [batch_to_cpu(b) for b in batches]
+        steps, warm = max(1, min(args.steps, 5)), 1
+        v, t_layer, B = cpu_reference_step(batches_cpu, args.cpu_branches, steps, warm, g.N)
+        sample = (f"oracle port (oracle/restate.py, sparse mapper), {args.cpu_branches}/32 branches of one hidden "
+                  f"layer (C=128) of the config-2 batch (B={B}), fwd+bwd+VQ update, scaled x{32 // args.cpu_branches}; "
+                  f"{steps} timed steps after {warm} warm-up")
+        line = {"impl": "reference", "metric": "train nodes/sec per VQ-GNN layer", "value": v,
+                "unit": "nodes/s/layer", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": t_layer * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "nodes/s/layer", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": sample},
+                "e2e": {"value": v, "unit": "nodes/s/layer", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import vq_gnn_b200 as V
+    from vq_gnn_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    _lib.require_device(torch.zeros(1, device=dev))
+    pk = peaks()
+
+    g, batches = build_workload(dev, rank, world, args.scale)
+    N = g.N
+    model = build_model(dev, N, distributed, args.assign_impl)
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, alpha=0.99)
+    warm_start(model, batches)
+    plans = [model.prepare(b[1]) for b in batches]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+
+    def flush_l2():
+        lib.vqgnn_flush_l2(_lib.ptr(flush), flush.numel(), _lib.stream())
+
+    def sync_all():
+        if distributed:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up, then exactly K steps, per-step CUDA events ----------
+    for i in range(args.warmup):
+        x, _, y = batches[i % len(batches)]
+        train_step(model, opt, x, plans[i % len(plans)], y, distributed)
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    for i in range(args.steps):
+        x, _, y = batches[i % len(batches)]
+        flush_l2()
+        ev[i][0].record()
+        train_step(model, opt, x, plans[i % len(plans)], y, distributed)
+        ev[i][1].record()
+    sync_all()
+    launches = _lib.launch_count() - l0 - args.steps   # minus the flush launches
+    clocks = sampler.stop()
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    nodes = torch.tensor([float(sum(batches[i % len(batches)][0].shape[0] for i in range(args.steps)))],
+                         dtype=torch.float64, device=dev)
+    if distributed:
+        torch.distributed.all_reduce(t_t, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(nodes)
+    t_ms = float(t_t.item())
+    ms_per_step = t_ms / args.steps
+    value = float(nodes.item()) * c["layers"] / (t_ms / 1e3)
+    model.check_status()
+
+    # ---- end-to-end through the public API from pinned host buffers ----------------------------
+    host = []
+    for x, bA, y in batches:
+        pin = lambda t: None if t is None else (tuple(u.cpu().pin_memory() for u in t) if isinstance(t, tuple)
+                                                else t.cpu().pin_memory())
+        host.append((x.cpu().pin_memory(), tuple(pin(t) for t in bA), y.cpu().pin_memory()))
+
+    def nbytes(t):
+        if t is None:
+            return 0
+        if isinstance(t, tuple):
+            return sum(nbytes(u) for u in t)
+        return t.numel() * t.element_size()
+    h2d = sum(nbytes(h[0]) + nbytes(h[1]) + nbytes(h[2]) for h in host) / len(host)
+
+    def to_dev(t):
+        if t is None:
+            return None
+        if isinstance(t, tuple):
+            return tuple(u.to(dev, non_blocking=True) for u in t)
+        return t.to(dev, non_blocking=True)
+
+    def e2e_step(i):
+        hx, hA, hy = host[i % len(host)]
+        x, y = hx.to(dev, non_blocking=True), hy.to(dev, non_blocking=True)   # the reference's prepare()
+        bA = tuple(to_dev(t) for t in hA)                                      # (v1/main_node.py:27-41)
+        loss = train_step(model, opt, x, bA, y, distributed)
+        return float(loss.item())                                              # D2H read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    sync_all()
+    e2e_ms = 0.0
+    for i in range(args.steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_step(i)
+        torch.cuda.synchronize()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    e_t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        torch.distributed.all_reduce(e_t, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = float(nodes.item()) * c["layers"] / (float(e_t.item()) / 1e3)
+
+    # ---- attribution pass: CUDA events around every C-ABI launch (dominant kernel + roofline) ---
+    roofline, kernel_table = None, {}
+    if rank == 0:
+        _lib.PROFILER.enabled = True
+        _lib.PROFILER.reset()
+        n_attr = min(args.steps, 8)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for i in range(n_attr):
+            x, _, y = batches[i % len(batches)]
+            flush_l2()
+            a0.record()
+            train_step(model, opt, x, plans[i % len(plans)], y, False if not distributed else distributed)
+            a1.record()
+            torch.cuda.synchronize()
+            tot += a0.elapsed_time(a1)
+        summ = _lib.PROFILER.summary()
+        _lib.PROFILER.enabled = False
+        summ.pop("vqgnn_flush_l2", None)
+        for k, (n, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+            kernel_table[k] = {"launches_per_step": n / n_attr, "ms_per_step": ms / n_attr,
+                               "share_of_step": (ms / n_attr) / (tot / n_attr)}
+        top = max(summ.items(), key=lambda kv: kv[1][1])[0]
+        # per-launch algorithmic work, summed over the launches of one step (3 layers), batch 0 shapes
+        plan0, B0 = plans[0], plans[0].B
+        work, bound = 0.0, "hbm"
+        for (cin, _cout) in [(c["C_in"], c["hidden"]), (c["hidden"], c["hidden"]), (c["hidden"], c["classes"])]:
+            w_, bound = algorithmic_work(top, plan0, cin, cin // c["D"], c["M"], B0)
+            work += w_
+        n_launch, ms_total = summ[top]
+        avg_ms = ms_total / n_launch
+        per_launch_work = work / (n_launch / n_attr)
+        if bound == "hbm":
+            achieved, peak, unit = per_launch_work / (avg_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+        else:
+            achieved, peak, unit = per_launch_work / (avg_ms * 1e-3) / 1e12, pk["tf_sust"], "TFLOP/s"
+        roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "traffic": None, "peak_source": pk["source"],
+                    "avg_launch_ms": avg_ms, "launches_per_step": n_launch / n_attr,
+                    "algorithmic_work_per_launch": per_launch_work}
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, t_layer, Bc = cpu_reference_step([batch_to_cpu(batches[0])], args.cpu_branches, 2, 1, N)
+        cpu_baseline = {"value": v, "unit": "nodes/s/layer", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"oracle port (oracle/restate.py, sparse mapper): {args.cpu_branches}/32 branches of "
+                                  f"one hidden layer (C=128) of the same batch (B={Bc}), fwd+bwd+VQ update, scaled "
+                                  f"x{32 // args.cpu_branches}; 2 timed steps after 1 warm-up; "
+                                  f"{t_layer * 1e3:.0f} ms per layer"}
+
+    if rank == 0:
+        line = {"metric": "train nodes/sec per VQ-GNN layer", "value": value, "unit": "nodes/s/layer",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "nodes/s/layer", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "kernels": kernel_table, "assign_impl": "tcgen05" if args.assign_impl == 1 else "simt-fp32"}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

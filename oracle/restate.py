@@ -218,6 +218,40 @@ def mapper_dense(batch_A, c: Tensor, num_M: int, gnn_type: str) -> Tensor:
     return adj
 
 
+def mapper_sparse(batch_A, c: Tensor, num_M: int, gnn_type: str) -> Tensor:
+    """Same matrix as `mapper_dense`, built the way the reference builds it: concatenate COO triples,
+    `coalesce` (sort + sum duplicates), drop values <= 0, add self loops, symmetrise
+    (vq_gnn_v1/utils/dataloader.py:144-192).  Returns a coalesced torch sparse COO tensor; this is the
+    form the CPU baseline times (the dense form is O((B+M)^2) memory)."""
+    deg_inv, A_BN, A_BB, A_NB_v, batch_idx = batch_A
+    B = batch_idx.shape[0]
+    dim = B + num_M
+    c = c.to(torch.long)
+    r, col, v = A_BN
+    cm = c[col] + B
+    rows, cols, vals = [r], [cm], [v]
+    if A_NB_v is not None:
+        rows.append(cm), cols.append(r), vals.append(A_NB_v)
+    if A_BB is not None:
+        br, bc, bv = A_BB
+        rows.append(br), cols.append(bc), vals.append(bv)
+        rows.append(br), cols.append(c[batch_idx[bc]] + B), vals.append(-bv)
+        if A_NB_v is not None:
+            rows.append(c[batch_idx[br]] + B), cols.append(bc), vals.append(-bv)
+    idx = torch.stack([torch.cat(rows), torch.cat(cols)])
+    adj = torch.sparse_coo_tensor(idx, torch.cat(vals), (dim, dim)).coalesce()
+    keep = adj.values() > 0
+    idx, vals = adj.indices()[:, keep], adj.values()[keep]
+    if gnn_type != 'SAGE':
+        i = torch.arange(B)
+        idx = torch.cat([idx, torch.stack([i, i])], 1)
+        vals = torch.cat([vals, deg_inv])
+    if gnn_type == 'GCN':
+        idx = torch.cat([idx, idx.flip(0)], 1)
+        vals = torch.cat([vals, vals])
+    return torch.sparse_coo_tensor(idx, vals, (dim, dim)).coalesce()
+
+
 # --------------------------------------------------------------------------------------
 # layer forward, v2 "B+B'" formulation  (vq_gnn_v2/models.py:144-231)
 # --------------------------------------------------------------------------------------
@@ -233,11 +267,14 @@ class OracleLayer:
     def __init__(self, in_channels: int, out_channels: int, num_M: int, num_D: int, num_N: int,
                  conv_type: str = 'GCN', version: str = 'v2', skip: bool = False,
                  grad_scale: Sequence[float] = (1, 1), warm_up_flag: bool = False,
-                 momentum: float = 0.1, hook_mode: str = 'fire'):
+                 momentum: float = 0.1, hook_mode: str = 'fire', sparse: bool = False,
+                 branches: Optional[Sequence[int]] = None):
         assert in_channels % num_D == 0, 'Cannot fully split'
         self.C, self.C_out, self.M, self.D, self.N = in_channels, out_channels, num_M, num_D, num_N
         self.nb = in_channels // num_D
         self.conv_type, self.version, self.skip, self.hook_mode = conv_type, version, skip, hook_mode
+        self.sparse = sparse          # v1 GCN/SAGE only: torch.sparse mapper + spmm (CPU-baseline form)
+        self.branches = branches      # bench sampling: run only these branches (outputs of the others are 0)
         add_flag = (version == 'v1' and conv_type == 'GAT')          # v1/models.py:53 ; v2/models.py:30
         self.vq: List[OracleVQ] = []
         self.c_indices: List[Tensor] = []
@@ -354,15 +391,23 @@ class OracleLayer:
         outs, info_total = [], 0
         for i in range(self.nb):
             X_B = x[:, D * i:D * (i + 1)]
+            if self.branches is not None and i not in self.branches:
+                outs.append(torch.zeros(B, D))
+                continue
             if self.training and (not self.inited or unlabeled):       # v1/models.py:149-165
                 idx = self.vq[i].feature_update(X_B.detach())
                 self.c_indices[i][batch_idx] = idx.squeeze(1).to(torch.short)
-            adj = mapper_dense(batch_A, self.c_indices[i], self.M, self.conv_type)   # :170
+            if self.sparse and self.conv_type != 'GAT':
+                adj = mapper_sparse(batch_A, self.c_indices[i], self.M, self.conv_type)
+            else:
+                adj = mapper_dense(batch_A, self.c_indices[i], self.M, self.conv_type)   # :170
             X_bar = self.vq[i].get_codebook().clone()                  # :173
             X_in = torch.cat([X_B, X_bar * wu], 0)                     # :181
             if self.conv_type == 'GAT':
                 X_in = torch.cat([X_in, torch.ones(X_in.shape[0], 1)], 1)    # :188-189
                 X_out = gat_propagate(adj, X_in, *self._att(i))
+            elif adj.is_sparse:
+                X_out = torch.sparse.mm(adj, X_in)
             else:
                 X_out = gcn_propagate(adj, X_in)
             X_out_B, X_out_M = X_out[:B], X_out[B:]                    # :197

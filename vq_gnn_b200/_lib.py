@@ -47,6 +47,54 @@ class VQGNNLibraryError(RuntimeError):
     pass
 
 
+class _Profiler:
+    """Optional per-kernel CUDA-event timing (bench.py's attribution pass).  Off by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []      # (name, start_event, stop_event, meta)
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b, _ in self.records:
+            d = out.setdefault(name, [0, 0.0])
+            d[0] += 1
+            d[1] += a.elapsed_time(b)
+        return out
+
+
+PROFILER = _Profiler()
+
+
+class _Proxy:
+    """Attribute access returns the ctypes function, wrapped with CUDA events while profiling."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not PROFILER.enabled or not name.startswith("vqgnn_") or name in _NO_STREAM:
+            return fn
+
+        def timed(*args):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            PROFILER.records.append((name, a, b, None))
+            return rc
+        return timed
+
+
+_NO_STREAM = {"vqgnn_abi_version", "vqgnn_arch_check", "vqgnn_last_error", "vqgnn_launch_count",
+              "vqgnn_mp_workspace_bytes"}
+
+
 def load():
     """dlopen libvqgnn.so (built in-tree by `make` / __graft_entry__.build())."""
     global _lib
@@ -63,8 +111,8 @@ def load():
         fn.restype, fn.argtypes = res, args
     if lib.vqgnn_abi_version() != 1:
         raise VQGNNLibraryError("libvqgnn.so ABI version mismatch")
-    _lib = lib
-    return lib
+    _lib = _Proxy(lib)
+    return _lib
 
 
 def last_error() -> str:
