@@ -112,30 +112,41 @@ int vqgnn_vq_finalize(const float* stats, int nb, int M, int D, int Dg, int Wp, 
  * vq_gnn_v1/utils/dataloader.py:144-192 (`mapper`) materialises (v1).
  * ------------------------------------------------------------------------------------------- */
 
+/* Work partition of a CSR for the message-passing kernels: the entries are cut into chunks of `chunk`
+ * consecutive entries (a multiple of 32) regardless of row boundaries, so power-law hub rows are spread
+ * over many warps.  chunk_row[c] = the row that entry c*chunk belongs to; vqgnn_mp_num_chunks() entries.
+ * Built once per mini-batch (per CSR) and reused by every layer. */
+int64_t vqgnn_mp_num_chunks(int64_t nnz, int chunk);
+int vqgnn_mp_chunk_rows(const int32_t* rowptr, int64_t R, int64_t nnz, int chunk, int32_t* chunk_row,
+                        void* stream);
+
 /* Forward over R rows of the plan's CSR (see vq_gnn_b200/graph.py: BatchPlan).  For row r:
  *   acc   = sum_e val[e] * (col[e] < B ? x[col[e], :] : feat_scale * O_k[code(node(col[e]-B), k), :D])
  *   gqacc = sum_{tail e} rval[e] * O_k[code(...), D:2D]                   (only if rval != NULL)
  * rows r <  B: y[r, :] = acc; gq[r, :] = gqacc; info += <x[r, :], gqacc>  (v1 info_backward, models.py:223)
  * rows r >= B: info += <acc, O_k[code(node(r-B), k), D:2D]>               (v2 info_backward, models.py:198)
- * *info = info_scale * info (fp64 accumulation, deterministic to fp32 rounding).
+ * *info = info_scale * info (fp64 accumulation over warps).
  * C = nb*D columns.  tail_node == NULL means identity.  info/gq may be NULL.
+ * chunk_row/chunk/nnz: the partition above for (rowptr, R).
  * ws: vqgnn_mp_workspace_bytes() bytes, zeroed by this call. */
 size_t vqgnn_mp_workspace_bytes(void);
-int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval, int64_t R,
-                 int64_t B, const float* x, int64_t ldx, const int32_t* tail_node, const int16_t* codes,
-                 const float* O, int nb, int M, int D, int Wp, float feat_scale, float info_scale,
-                 float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws, void* stream);
+int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
+                 const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B, const float* x,
+                 int64_t ldx, const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M,
+                 int D, int Wp, float feat_scale, float info_scale, float* y, int64_t ldy, float* gq,
+                 int64_t ldgq, float* info, void* ws, void* stream);
 
 /* Backward of the same: for batch column j < B
  *   dx[j, :] = sum_e bval[e] * (brow[e] < B ? dy[brow[e], :]
  *                                           : tail_scale * (*dinfo) * O_k[code(node(brow[e]-B), k), D:2D])
  *              + gq_scale * (*dinfo) * gq[j, :]        (if gq != NULL; v1)
  * i.e. adj^T @ dY restricted to batch rows plus the gradient of info_backward.
- * dinfo is a device scalar (NULL = 1). */
-int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval, int64_t B, const float* dy,
-                 int64_t lddy, const int32_t* tail_node, const int16_t* codes, const float* O, int nb,
-                 int M, int D, int Wp, float tail_scale, const float* gq, int64_t ldgq, float gq_scale,
-                 const float* dinfo, float* dx, int64_t lddx, void* stream);
+ * dinfo is a device scalar (NULL = 1).  chunk_row/chunk/nnz: the partition of (browptr, B). */
+int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval, const int32_t* chunk_row,
+                 int chunk, int64_t nnz, int64_t B, const float* dy, int64_t lddy, const int32_t* tail_node,
+                 const int16_t* codes, const float* O, int nb, int M, int D, int Wp, float tail_scale,
+                 const float* gq, int64_t ldgq, float gq_scale, const float* dinfo, float* dx, int64_t lddx,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * helpers

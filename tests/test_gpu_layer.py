@@ -176,3 +176,29 @@ def test_full_model_train_step_matches_oracle_stack():
         for li, o in enumerate(oracles):
             bad, n_codes = H.state_mismatches(model.convs[li].state_dict(), o.state_dict(), 5 * REL_TOL)
             assert not bad and n_codes == 0, (version, li, bad, n_codes)
+
+
+@pytest.mark.parametrize("version,conv", [("v1", "SAGE"), ("v1", "GCN"), ("v2", "GCN"), ("v2", "SAGE")])
+def test_hub_rows_cut_by_chunk_boundaries(version, conv):
+    """Power-law graph whose hub rows hold thousands of entries (>> the 256-entry warp chunk of the
+    message-passing kernels) next to empty rows: exercises the RED-accumulated partial rows."""
+    dev = torch.device("cuda:0")
+    N, B, M, C, D = 3000, 400, 32, 8, 4
+    g = H.make_graph(N, 150_000, conv, version, seed=21, power_law=1.2)
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    assert int(deg.max()) > 1024
+    hubs = torch.argsort(deg, descending=True)[:B // 2]
+    gen = torch.Generator().manual_seed(5)
+    rest = torch.randperm(N, generator=gen)
+    rest = rest[~torch.isin(rest, hubs)][:B - hubs.numel()]
+    node_idx = torch.cat([hubs, rest])[torch.randperm(B, generator=gen)]
+    from vq_gnn_b200 import sampling
+    batch_A = (sampling.k_hop_batch_v2(g, node_idx, True) if version == "v2"
+               else sampling.collate_batch_v1(g, node_idx, True, True))
+    torch.manual_seed(13)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, 6, M, D, N, conv), version=version)
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, 6, M, D, N, conv, version, warm_up_flag=True).load_state_dict(sd)
+    layer = layer.to(dev)
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    _compare(_run_cuda(layer, batch_A, x, 3, dev), _run_oracle(o, batch_A, x, 3), layer, o)

@@ -33,10 +33,12 @@ _SIGNATURES = {
     "vqgnn_vq_finalize": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, f64, i32, f32, f32, f32, vp, vp, vp, vp,
                                     vp, vp, vp, vp, vp, vp]),
     "vqgnn_mp_workspace_bytes": (C.c_size_t, []),
-    "vqgnn_mp_fwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, f32, f32,
-                               vp, i64, vp, i64, vp, vp, vp]),
-    "vqgnn_mp_bwd": (C.c_int, [vp, vp, vp, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, f32, vp, i64, f32,
-                               vp, vp, i64, vp]),
+    "vqgnn_mp_num_chunks": (i64, [i64, i32]),
+    "vqgnn_mp_chunk_rows": (C.c_int, [vp, i64, i64, i32, vp, vp]),
+    "vqgnn_mp_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32,
+                               f32, f32, vp, i64, vp, i64, vp, vp, vp]),
+    "vqgnn_mp_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, f32,
+                               vp, i64, f32, vp, vp, i64, vp]),
     "vqgnn_fill_zero": (C.c_int, [vp, C.c_size_t, vp]),
     "vqgnn_flush_l2": (C.c_int, [vp, C.c_size_t, vp]),
     "vqgnn_codes_pack": (C.c_int, [vp, i32, i64, vp, vp]),
@@ -92,7 +94,7 @@ class _Proxy:
 
 
 _NO_STREAM = {"vqgnn_abi_version", "vqgnn_arch_check", "vqgnn_last_error", "vqgnn_launch_count",
-              "vqgnn_mp_workspace_bytes"}
+              "vqgnn_mp_workspace_bytes", "vqgnn_mp_num_chunks"}
 
 
 def load():

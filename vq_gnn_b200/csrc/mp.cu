@@ -1,34 +1,24 @@
-// VQ-approximated message passing, GCN / SAGE-Mean: gather-SpMM over the batch plan.
-// One warp per (output row, 32*VEC-column slab).  In-batch neighbours read dense rows (coalesced
-// 16 B per lane); out-of-batch neighbours read the node's code row (2 B per lane, one 64 B line at
-// nb = 32) and gather their codeword from the L2-resident codebook.  HBM-bound integer/float gather
-// work: no tensor cores.  Reference maths: vq_gnn_v2/models.py:161-198, vq_gnn_v2/convs.py:65-101,
+// VQ-approximated message passing, GCN / SAGE-Mean: nnz-balanced gather-SpMM over the batch plan.
+//
+// Work unit = one warp x (chunk of `chunk` consecutive CSR entries) x (slab of 32*VEC columns).  Chunks ignore
+// row boundaries, so a power-law hub row (10^4..10^5 entries in the Reddit-shaped batch) is spread over
+// hundreds of warps instead of serialising one (the first version of this kernel was row-per-warp and spent
+// 30 ms in its longest row).  Rows that lie wholly inside a chunk are stored directly; rows cut by a chunk
+// boundary are accumulated with vector REDs (red.global.add.v4.f32) into a pre-zeroed output.
+//
+// In-batch neighbours read dense rows (coalesced 16 B per lane); out-of-batch neighbours read the node's code
+// row (2 B per lane, contiguous over the branches of the slab) and gather their codeword from the L2-resident
+// codebook -- one 32 B sector per (entry, branch), fetched with a single 256-bit load when both the feature
+// and the gradient half are needed.  HBM/L2-bound integer+float gather work: no tensor cores.
+//
+// Reference maths: vq_gnn_v2/models.py:161-198, vq_gnn_v2/convs.py:65-101,
 // vq_gnn_v1/models.py:170-223 + vq_gnn_v1/utils/dataloader.py:144-192.
 #include "common.cuh"
 
 namespace vqgnn {
 
 constexpr int kMpWarps = 8;
-
-template <int VEC>
-struct Vec;
-template <>
-struct Vec<4> {
-  float v[4];
-  __device__ __forceinline__ void load(const float* p) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-  }
-  __device__ __forceinline__ void store(float* p) const {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-};
-template <>
-struct Vec<1> {
-  float v[1];
-  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
-  __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
-};
+constexpr int kMpUnroll = 4;
 
 struct Codebook {
   const int32_t* tail_node;  // [T] or nullptr (identity)
@@ -37,79 +27,155 @@ struct Codebook {
   int nb, M, D, Wp;
 };
 
-// Accumulate one CSR row for the lane's VEC columns starting at column c0 (branch k, offset off).
+template <int VEC>
+__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = __ldg(p + i);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = v[i];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void red_vec(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3])
+                 : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) atomicAdd(p + i, v[i]);
+  }
+}
+// one 32 B sector: feature half -> a, gradient half -> b (Wp == 8, D == 4)
+__device__ __forceinline__ void ld_sector(const float* p, float (&a)[4], float (&b)[4]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3])
+               : "l"(p));
+}
+
+// Walks one chunk [eb, ee) of the CSR for the lane's VEC columns starting at c0 (branch k, offset off) and
+// calls flush(row, acc, gqa, whole) at every row end inside the chunk and once for a trailing partial row
+// (whole = the row starts and ends inside this chunk, so no other warp touches its output).
 //   acc += val * (src < B ? dense[src, c0..] : tscale * O_k[code, half_off + off ..])
-//   gqa += rval * O_k[code, D + off ..]     (HAS_GQ, tail entries only)
-template <int VEC, bool HAS_GQ>
-__device__ __forceinline__ void gather_row(int e0, int e1, const int32_t* __restrict__ col,
-                                           const float* __restrict__ val, const float* __restrict__ rval,
-                                           int B, const float* __restrict__ dense, int64_t ldd,
-                                           const Codebook& cb, int half_off, float tscale, bool active,
-                                           int c0, int k, int off, int lane, float (&acc)[VEC],
-                                           float (&gqa)[VEC]) {
-  constexpr int U = 4;
-  for (int eb = e0; eb < e1; eb += 32) {
-    const int e = eb + lane;
+//   gqa += rval * O_k[code, D + off ..]                                  (HAS_GQ, tail entries only)
+// WIDE: VEC == 4, HAS_GQ, Wp == 8, D == 4, half_off == 0 -> one 256-bit load per gathered codeword.
+template <int VEC, bool HAS_GQ, bool WIDE, class Flush>
+__device__ __forceinline__ void walk_chunk(int eb, int ee, int r, int64_t R,
+                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                           const float* __restrict__ val, const float* __restrict__ rval, int B,
+                                           const float* __restrict__ dense, int64_t ldd, const Codebook& cb,
+                                           int half_off, float tscale, bool active, int c0, int k, int off,
+                                           int lane, Flush&& flush) {
+  constexpr int U = kMpUnroll;
+  float acc[VEC], gqa[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
+  // row boundaries: lane i holds rowptr[rbase + i]; row r is [shfl(r - rbase), shfl(r - rbase + 1))
+  int rbase = r;
+  int rp_l = __ldg(rowptr + min(static_cast<int64_t>(rbase) + lane, R));
+  int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
+  bool pending = false;
+
+  for (int bb = eb; bb < ee; bb += 32) {
+    const int e = bb + lane;
     int c_l = -1, node_l = 0;
     float v_l = 0.f, rv_l = 0.f;
-    if (e < e1) {
+    if (e < ee) {
       c_l = __ldg(col + e);
       v_l = __ldg(val + e);
       if (HAS_GQ) rv_l = __ldg(rval + e);
       if (c_l >= B) node_l = cb.tail_node ? __ldg(cb.tail_node + (c_l - B)) : (c_l - B);
     }
-    const int cnt = min(32, e1 - eb);
-    for (int j = 0; j < cnt; j += U) {
-      int c[U], node[U];
-      float v[U], rv[U];
+    const int cnt = min(32, ee - bb);
+    int j = 0;
+    while (j < cnt) {
+      const int jend = min(cnt, re - bb);  // entries of row r inside this batch end here
+      for (; j < jend; j += U) {
+        int c[U], node[U];
+        float v[U], rv[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int src_lane = min(j + u, 31);
-        c[u] = __shfl_sync(0xffffffffu, c_l, src_lane);
-        v[u] = __shfl_sync(0xffffffffu, v_l, src_lane);
-        node[u] = __shfl_sync(0xffffffffu, node_l, src_lane);
-        rv[u] = HAS_GQ ? __shfl_sync(0xffffffffu, rv_l, src_lane) : 0.f;
-        if (j + u >= cnt) c[u] = -1;
-      }
-      if (!active) continue;
-      const float* p[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {  // first level: code loads for tail entries (independent)
-        p[u] = nullptr;
-        if (c[u] >= B) {
-          const int code = __ldg(cb.codes + static_cast<int64_t>(node[u]) * cb.nb + k);
-          p[u] = cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + off;
-        } else if (c[u] >= 0) {
-          p[u] = dense + static_cast<int64_t>(c[u]) * ldd + c0;
+        for (int u = 0; u < U; ++u) {
+          const int src_lane = min(j + u, 31);
+          c[u] = __shfl_sync(0xffffffffu, c_l, src_lane);
+          v[u] = __shfl_sync(0xffffffffu, v_l, src_lane);
+          node[u] = __shfl_sync(0xffffffffu, node_l, src_lane);
+          rv[u] = HAS_GQ ? __shfl_sync(0xffffffffu, rv_l, src_lane) : 0.f;
+          if (j + u >= jend) c[u] = -1;
         }
-      }
-      Vec<VEC> a[U], gq[U];
+        if (!active) continue;
+        const float* p[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {  // second level: the gathers
-        if (c[u] >= B) {
-          a[u].load(p[u] + half_off);
-          if (HAS_GQ) gq[u].load(p[u] + cb.D);
-        } else if (c[u] >= 0) {
-          a[u].load(p[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (c[u] >= B) {
-          const float s = v[u] * tscale;
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s, a[u].v[i], acc[i]);
-          if (HAS_GQ) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) gqa[i] = fmaf(rv[u], gq[u].v[i], gqa[i]);
+        for (int u = 0; u < U; ++u) {  // first level: code loads for tail entries (independent)
+          p[u] = nullptr;
+          if (c[u] >= B) {
+            const int code = __ldg(cb.codes + static_cast<int64_t>(node[u]) * cb.nb + k);
+            p[u] = cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + off;
+          } else if (c[u] >= 0) {
+            p[u] = dense + static_cast<int64_t>(c[u]) * ldd + c0;
           }
-        } else if (c[u] >= 0) {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(v[u], a[u].v[i], acc[i]);
         }
+        float a[U][VEC], g[U][VEC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // second level: the gathers
+          if (c[u] >= B) {
+            if constexpr (WIDE) {
+              ld_sector(p[u], a[u], g[u]);
+            } else {
+              ld_vec<VEC>(p[u] + half_off, a[u]);
+              if (HAS_GQ) ld_vec<VEC>(p[u] + cb.D, g[u]);
+            }
+          } else if (c[u] >= 0) {
+            ld_vec<VEC>(p[u], a[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (c[u] >= B) {
+            const float s = v[u] * tscale;
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s, a[u][i], acc[i]);
+            if (HAS_GQ) {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) gqa[i] = fmaf(rv[u], g[u][i], gqa[i]);
+            }
+          } else if (c[u] >= 0) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(v[u], a[u][i], acc[i]);
+          }
+        }
+      }
+      j = jend;
+      pending = true;
+      if (bb + j == re) {  // row r is complete
+        flush(r, acc, gqa, rs >= eb);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
+        pending = false;
+        if (bb + j >= ee) break;
+        do {  // next non-empty row (empty rows keep the pre-initialised output)
+          ++r;
+          if (r - rbase >= 31) {
+            rbase = r;
+            rp_l = __ldg(rowptr + min(static_cast<int64_t>(rbase) + lane, R));
+          }
+          rs = __shfl_sync(0xffffffffu, rp_l, r - rbase);
+          re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
+        } while (re <= bb + j);
       }
     }
   }
+  if (pending) flush(r, acc, gqa, false);
 }
 
 // block-level fp64 reduction of the info partials + "last block finishes" epilogue
@@ -134,94 +200,134 @@ __device__ __forceinline__ void info_reduce(double part, double* ws_sum, unsigne
   }
 }
 
-template <int VEC, bool HAS_GQ>
+// chunk c starts at entry c*chunk; chunk_row[c] = the row that entry belongs to
+__global__ void mp_chunk_rows_kernel(const int32_t* __restrict__ rowptr, int64_t R, int64_t nnz, int chunk,
+                                     int n_chunks, int32_t* __restrict__ chunk_row) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const int64_t e = static_cast<int64_t>(c) * chunk;
+  int64_t lo = 0, hi = R;  // largest r with rowptr[r] <= e  (rowptr[0] = 0 <= e < nnz = rowptr[R])
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(rowptr + mid) <= e) lo = mid;
+    else hi = mid;
+  }
+  chunk_row[c] = static_cast<int32_t>(lo);
+}
+
+template <int VEC, bool HAS_GQ, bool WIDE>
 __global__ void __launch_bounds__(kMpWarps * 32)
     mp_fwd_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                  const float* __restrict__ val, const float* __restrict__ rval, int64_t R, int B,
+                  const float* __restrict__ val, const float* __restrict__ rval,
+                  const int32_t* __restrict__ chunk_row, int n_chunks, int chunk, int nnz, int64_t R, int B,
                   const float* __restrict__ x, int64_t ldx, Codebook cb, int C, int nslab, float feat_scale,
                   float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ gq, int64_t ldgq,
                   float* __restrict__ info, double* ws_sum, unsigned int* ws_count) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
   double part = 0.0;
-  if (task < R * nslab) {
-    const int64_t r = task / nslab;
-    const int slab = static_cast<int>(task - r * nslab);
+  if (task < static_cast<int64_t>(n_chunks) * nslab) {
+    // slab-major order: the warps of a CTA share a slab (same codebook branches -> L1/L2 locality)
+    const int slab = static_cast<int>(task / n_chunks);
+    const int ch = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
     const int c0 = (slab * 32 + lane) * VEC;
     const bool active = c0 < C;
     const int k = active ? c0 / cb.D : 0, off = active ? c0 - k * cb.D : 0;
-    float acc[VEC], gqa[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
-    gather_row<VEC, HAS_GQ>(__ldg(rowptr + r), __ldg(rowptr + r + 1), col, val, rval, B, x, ldx, cb, 0,
-                            feat_scale, active, c0, k, off, lane, acc, gqa);
-    if (active) {
+    const int eb = ch * chunk, ee = min(eb + chunk, nnz);
+    float fpart = 0.f;
+    auto flush = [&](int r, float (&acc)[VEC], float (&gqa)[VEC], bool whole) {
+      if (!active) return;
       if (r < B) {
-        Vec<VEC> o;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
-        o.store(y + r * ldy + c0);
+        float* yp = y + static_cast<int64_t>(r) * ldy + c0;
+        if (whole) st_vec<VEC>(yp, acc);
+        else red_vec<VEC>(yp, acc);
         if (HAS_GQ) {
-          Vec<VEC> q, xr;
+          if (gq) {
+            float* gp = gq + static_cast<int64_t>(r) * ldgq + c0;
+            if (whole) st_vec<VEC>(gp, gqa);
+            else red_vec<VEC>(gp, gqa);
+          }
+          if (info) {  // v1: <x[r], gq[r]>  (vq_gnn_v1/models.py:223 rewritten row-wise)
+            float xr[VEC];
+            ld_vec<VEC>(x + static_cast<int64_t>(r) * ldx + c0, xr);
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) q.v[i] = gqa[i];
-          if (gq) q.store(gq + r * ldgq + c0);
-          xr.load(x + r * ldx + c0);
-          float d = 0.f;
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) d = fmaf(xr.v[i], gqa[i], d);
-          part = d;
+            for (int i = 0; i < VEC; ++i) fpart = fmaf(xr[i], gqa[i], fpart);
+          }
         }
-      } else if (info) {  // v2: <Y[r], Gq[r]> with Gq the node's own gradient codeword
-        const int node = cb.tail_node ? __ldg(cb.tail_node + (r - B)) : static_cast<int>(r - B);
+      } else if (info) {  // v2: <Y[r], Gq[r]> with Gq the node's own gradient codeword (models.py:198)
+        const int node = cb.tail_node ? __ldg(cb.tail_node + (r - B)) : (r - B);
         const int code = __ldg(cb.codes + static_cast<int64_t>(node) * cb.nb + k);
-        Vec<VEC> gv;
-        gv.load(cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + cb.D + off);
-        float d = 0.f;
+        float gv[VEC];
+        ld_vec<VEC>(cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + cb.D + off, gv);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) d = fmaf(acc[i], gv.v[i], d);
-        part = d;
+        for (int i = 0; i < VEC; ++i) fpart = fmaf(acc[i], gv[i], fpart);
       }
-    }
+    };
+    walk_chunk<VEC, HAS_GQ, WIDE>(eb, ee, __ldg(chunk_row + ch), R, rowptr, col, val, rval, B, x, ldx, cb, 0,
+                                  feat_scale, active, c0, k, off, lane, flush);
+    part = static_cast<double>(fpart);
   }
   if (info) info_reduce(part, ws_sum, ws_count, info_scale, info);
+}
+
+// dx <- gq_scale * dinfo * gq  (or 0): the part of the backward that does not depend on the CSR
+template <int VEC>
+__global__ void mp_bwd_init_kernel(int64_t B, int C, const float* __restrict__ gq, int64_t ldgq, float gq_scale,
+                                   const float* __restrict__ dinfo, float* __restrict__ dx, int64_t lddx) {
+  const int cv = C / VEC;
+  const int64_t n = B * cv;
+  const float s = gq ? gq_scale * (dinfo ? __ldg(dinfo) : 1.f) : 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t r = i / cv;
+    const int c = static_cast<int>(i - r * cv) * VEC;
+    float q[VEC];
+    if (gq) {
+      ld_vec<VEC>(gq + r * ldgq + c, q);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) q[j] *= s;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) q[j] = 0.f;
+    }
+    st_vec<VEC>(dx + r * lddx + c, q);
+  }
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(kMpWarps * 32)
     mp_bwd_kernel(const int32_t* __restrict__ browptr, const int32_t* __restrict__ brow,
-                  const float* __restrict__ bval, int B, const float* __restrict__ dy, int64_t lddy,
-                  Codebook cb, int C, int nslab, float tail_scale, const float* __restrict__ gq, int64_t ldgq,
-                  float gq_scale, const float* __restrict__ dinfo, float* __restrict__ dx, int64_t lddx) {
+                  const float* __restrict__ bval, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
+                  int nnz, int B, const float* __restrict__ dy, int64_t lddy, Codebook cb, int C, int nslab,
+                  float tail_scale, const float* __restrict__ dinfo, float* __restrict__ dx, int64_t lddx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
-  if (task >= static_cast<int64_t>(B) * nslab) return;
-  const int64_t j = task / nslab;
-  const int slab = static_cast<int>(task - j * nslab);
+  if (task >= static_cast<int64_t>(n_chunks) * nslab) return;
+  const int slab = static_cast<int>(task / n_chunks);
+  const int ch = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
   const int c0 = (slab * 32 + lane) * VEC;
   const bool active = c0 < C;
   const int k = active ? c0 / cb.D : 0, off = active ? c0 - k * cb.D : 0;
   const float di = dinfo ? __ldg(dinfo) : 1.f;
-  float acc[VEC], unused[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f, unused[i] = 0.f;
-  gather_row<VEC, false>(__ldg(browptr + j), __ldg(browptr + j + 1), brow, bval, nullptr, B, dy, lddy, cb,
-                         cb.D, tail_scale * di, active, c0, k, off, lane, acc, unused);
-  if (!active) return;
-  if (gq) {
-    Vec<VEC> q;
-    q.load(gq + j * ldgq + c0);
-    const float s = gq_scale * di;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s, q.v[i], acc[i]);
-  }
-  Vec<VEC> o;
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
-  o.store(dx + j * lddx + c0);
+  const int eb = ch * chunk, ee = min(eb + chunk, nnz);
+  auto flush = [&](int j, float (&acc)[VEC], float (&)[VEC], bool) {
+    if (active) red_vec<VEC>(dx + static_cast<int64_t>(j) * lddx + c0, acc);  // onto the initialised dx
+  };
+  walk_chunk<VEC, false, false>(eb, ee, __ldg(chunk_row + ch), B, browptr, brow, bval, nullptr, B, dy, lddy, cb,
+                                cb.D, tail_scale * di, active, c0, k, off, lane, flush);
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+static int zero_rows(float* p, int64_t rows, int C, int64_t ld, cudaStream_t s) {
+  if (ld == C) {
+    VQ_CUDA(cudaMemsetAsync(p, 0, sizeof(float) * rows * C, s));
+  } else {
+    VQ_CUDA(cudaMemset2DAsync(p, sizeof(float) * ld, 0, sizeof(float) * C, rows, s));
+  }
+  return VQGNN_OK;
+}
 
 }  // namespace vqgnn
 
@@ -229,64 +335,103 @@ using namespace vqgnn;
 
 extern "C" size_t vqgnn_mp_workspace_bytes(void) { return 64; }
 
+extern "C" int64_t vqgnn_mp_num_chunks(int64_t nnz, int chunk) {
+  return chunk > 0 ? (nnz + chunk - 1) / chunk : -1;
+}
+
+extern "C" int vqgnn_mp_chunk_rows(const int32_t* rowptr, int64_t R, int64_t nnz, int chunk, int32_t* chunk_row,
+                                   void* stream) {
+  VQ_CHECK_ARG(rowptr && R > 0 && nnz >= 0 && chunk > 0 && chunk % 32 == 0, "mp_chunk_rows: bad arguments");
+  VQ_CHECK_ARG(nnz < (1ll << 31), "mp_chunk_rows: nnz must fit int32");
+  const int n_chunks = static_cast<int>(vqgnn_mp_num_chunks(nnz, chunk));
+  if (n_chunks == 0) return VQGNN_OK;
+  VQ_CHECK_ARG(chunk_row, "mp_chunk_rows: null output");
+  mp_chunk_rows_kernel<<<ceil_div(n_chunks, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rowptr, R, nnz, chunk, n_chunks, chunk_row);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}
+
 extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
-                            int64_t R, int64_t B, const float* x, int64_t ldx, const int32_t* tail_node,
-                            const int16_t* codes, const float* O, int nb, int M, int D, int Wp, float feat_scale,
-                            float info_scale, float* y, int64_t ldy, float* gq, int64_t ldgq, float* info,
-                            void* ws, void* stream) {
+                            const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
+                            const float* x, int64_t ldx, const int32_t* tail_node, const int16_t* codes,
+                            const float* O, int nb, int M, int D, int Wp, float feat_scale, float info_scale,
+                            float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws,
+                            void* stream) {
   VQ_CHECK_ARG(rowptr && col && val && x && codes && O && y, "mp_fwd: null argument");
   VQ_CHECK_ARG(R >= B && B > 0 && nb > 0 && D > 0 && Wp >= 2 * D, "mp_fwd: bad sizes");
   VQ_CHECK_ARG(!info || ws, "mp_fwd: info needs a workspace");
-  VQ_CHECK_ARG(B < (1ll << 31) && R < (1ll << 31), "mp_fwd: too many rows");
+  VQ_CHECK_ARG(B < (1ll << 31) && R < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "mp_fwd: sizes must fit int32");
+  VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_fwd: needs chunk_row (vqgnn_mp_chunk_rows)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C = nb * D;
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
   double* ws_sum = static_cast<double*>(ws);
   unsigned int* ws_count = ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 8) : nullptr;
   if (info) VQ_CUDA(cudaMemsetAsync(ws, 0, 16, s));
-  const bool vec4 = (D % 4 == 0) && (Wp % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(x) &&
+  // rows cut by a chunk boundary accumulate with REDs, empty rows are never visited: start from zero
+  if (int rc = zero_rows(y, B, C, ldy, s)) return rc;
+  if (gq && rval)
+    if (int rc = zero_rows(gq, B, C, ldgq, s)) return rc;
+  const int n_chunks = static_cast<int>(vqgnn_mp_num_chunks(nnz, chunk));
+  if (n_chunks == 0) {
+    if (info) VQ_CUDA(cudaMemsetAsync(info, 0, sizeof(float), s));
+    return VQGNN_OK;
+  }
+  const bool vec4 = (D == 4) && (Wp % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(x) &&
                     aligned16(y) && aligned16(O) && (!gq || (ldgq % 4 == 0 && aligned16(gq)));
+  const bool wide = vec4 && rval && Wp == 8 && aligned32(O);
   const int vec = vec4 ? 4 : 1;
   const int nslab = ceil_div(C, 32 * vec);
-  const int64_t tasks = R * nslab;
+  const int64_t tasks = static_cast<int64_t>(n_chunks) * nslab;
   const int grid = ceil_div(tasks, kMpWarps);
-#define VQ_MP_FWD(VEC, GQ)                                                                                  \
-  mp_fwd_kernel<VEC, GQ><<<grid, kMpWarps * 32, 0, s>>>(rowptr, col, val, rval, R, (int)B, x, ldx, cb, C,   \
-                                                        nslab, feat_scale, info_scale, y, ldy, gq, ldgq,    \
-                                                        info, ws_sum, ws_count)
+#define VQ_MP_FWD(VEC, GQ, WIDE)                                                                              \
+  mp_fwd_kernel<VEC, GQ, WIDE><<<grid, kMpWarps * 32, 0, s>>>(rowptr, col, val, rval, chunk_row, n_chunks,    \
+                                                              chunk, (int)nnz, R, (int)B, x, ldx, cb, C, nslab, \
+                                                              feat_scale, info_scale, y, ldy, gq, ldgq, info, \
+                                                              ws_sum, ws_count)
   if (vec4) {
-    if (rval) VQ_MP_FWD(4, true);
-    else VQ_MP_FWD(4, false);
+    if (wide) VQ_MP_FWD(4, true, true);
+    else if (rval) VQ_MP_FWD(4, true, false);
+    else VQ_MP_FWD(4, false, false);
   } else {
-    if (rval) VQ_MP_FWD(1, true);
-    else VQ_MP_FWD(1, false);
+    if (rval) VQ_MP_FWD(1, true, false);
+    else VQ_MP_FWD(1, false, false);
   }
 #undef VQ_MP_FWD
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }
 
-extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval, int64_t B,
-                            const float* dy, int64_t lddy, const int32_t* tail_node, const int16_t* codes,
-                            const float* O, int nb, int M, int D, int Wp, float tail_scale, const float* gq,
-                            int64_t ldgq, float gq_scale, const float* dinfo, float* dx, int64_t lddx,
-                            void* stream) {
+extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
+                            const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* dy,
+                            int64_t lddy, const int32_t* tail_node, const int16_t* codes, const float* O, int nb,
+                            int M, int D, int Wp, float tail_scale, const float* gq, int64_t ldgq,
+                            float gq_scale, const float* dinfo, float* dx, int64_t lddx, void* stream) {
   VQ_CHECK_ARG(browptr && brow && bval && dy && codes && O && dx, "mp_bwd: null argument");
   VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && nb > 0 && D > 0 && Wp >= 2 * D, "mp_bwd: bad sizes");
+  VQ_CHECK_ARG(nnz >= 0 && nnz < (1ll << 31), "mp_bwd: nnz must fit int32");
+  VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_bwd: needs chunk_row (vqgnn_mp_chunk_rows)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C = nb * D;
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
-  const bool vec4 = (D % 4 == 0) && (Wp % 4 == 0) && (lddy % 4 == 0) && (lddx % 4 == 0) && aligned16(dy) &&
+  const bool vec4 = (D == 4) && (Wp % 4 == 0) && (lddy % 4 == 0) && (lddx % 4 == 0) && aligned16(dy) &&
                     aligned16(dx) && aligned16(O) && (!gq || (ldgq % 4 == 0 && aligned16(gq)));
   const int vec = vec4 ? 4 : 1;
   const int nslab = ceil_div(C, 32 * vec);
-  const int grid = ceil_div(B * nslab, kMpWarps);
+  const int n_chunks = static_cast<int>(vqgnn_mp_num_chunks(nnz, chunk));
+  const int init_grid = static_cast<int>(std::min<int64_t>((B * (C / vec) + 255) / 256, 8 * kNumSMs));
+  if (vec4) mp_bwd_init_kernel<4><<<init_grid, 256, 0, s>>>(B, C, gq, ldgq, gq_scale, dinfo, dx, lddx);
+  else mp_bwd_init_kernel<1><<<init_grid, 256, 0, s>>>(B, C, gq, ldgq, gq_scale, dinfo, dx, lddx);
+  VQ_LAUNCH_CHECK();
+  if (n_chunks == 0) return VQGNN_OK;
+  const int grid = ceil_div(static_cast<int64_t>(n_chunks) * nslab, kMpWarps);
   if (vec4)
-    mp_bwd_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, (int)B, dy, lddy, cb, C, nslab,
-                                                    tail_scale, gq, ldgq, gq_scale, dinfo, dx, lddx);
+    mp_bwd_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, chunk_row, n_chunks, chunk, (int)nnz,
+                                                    (int)B, dy, lddy, cb, C, nslab, tail_scale, dinfo, dx, lddx);
   else
-    mp_bwd_kernel<1><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, (int)B, dy, lddy, cb, C, nslab,
-                                                    tail_scale, gq, ldgq, gq_scale, dinfo, dx, lddx);
+    mp_bwd_kernel<1><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, chunk_row, n_chunks, chunk, (int)nnz,
+                                                    (int)B, dy, lddy, cb, C, nslab, tail_scale, dinfo, dx, lddx);
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }

@@ -118,6 +118,26 @@ class BatchPlan:
     def nnz(self) -> int:
         return int(self.fwd_col.numel())
 
+    def chunk_rows(self, which: str) -> Tensor:
+        """nnz-balanced work partition of the forward ('fwd') or transposed ('bwd') CSR for the CUDA
+        kernels (include/vqgnn.h: vqgnn_mp_chunk_rows).  Built lazily on the device, once per plan."""
+        key = 'chunk_rows_' + which
+        t = self.extras.get(key)
+        if t is None:
+            from . import _lib
+            rowptr, nnz, rows = ((self.fwd_rowptr, self.nnz, self.R) if which == 'fwd'
+                                 else (self.bwd_rowptr, int(self.bwd_col.numel()), self.B))
+            _lib.require_device(rowptr)
+            lib = _lib.load()
+            n = int(lib.vqgnn_mp_num_chunks(nnz, MP_CHUNK))
+            t = torch.empty(max(n, 1), dtype=torch.int32, device=rowptr.device)
+            _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(rowptr), rows, nnz, MP_CHUNK, _lib.ptr(t), _lib.stream()))
+            self.extras[key] = t
+        return t
+
+
+MP_CHUNK = 256   # CSR entries per warp task (multiple of 32)
+
 
 def _i32(t: Tensor) -> Tensor:
     return t.to(torch.int32).contiguous()

@@ -25,7 +25,7 @@ from torch import nn
 
 from . import _lib
 from .convs import OurGATConv, OurGCNConv, Transformer  # noqa: F401
-from .graph import BatchPlan, CSRAdj, build_plan
+from .graph import MP_CHUNK, BatchPlan, CSRAdj, build_plan
 from .vq import VectorQuantizerEMA, VQBank
 
 Tensor = torch.Tensor
@@ -75,7 +75,7 @@ class VQConvFunction(torch.autograd.Function):
         ws = _mp_ws(dev) if need_info else None
         _lib.check(lib.vqgnn_mp_fwd(
             _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
-            plan.R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
+            _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
             _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, float(wu) if v1 else 1.0, float(wu),
             _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
             _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
@@ -97,7 +97,8 @@ class VQConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, C, device=x.device)
             _lib.check(lib.vqgnn_mp_bwd(
-                _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val), B, _lib.ptr(dy),
+                _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
+                _lib.ptr(plan.chunk_rows('bwd')), MP_CHUNK, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
                 dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
                 bank.M, bank.D, bank.Wp, 0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
                 wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0), st))
@@ -122,8 +123,12 @@ def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Ten
     codes = torch.zeros(1, 1, dtype=torch.int16, device=x.device)
     O = torch.zeros(1, 1, 8, device=x.device)
     D = 4 if C % 4 == 0 else 1
+    rowptr, col, val = rowptr.to(torch.int32), col.to(torch.int32), val.float().contiguous()
+    nnz = int(col.numel())
+    chunks = torch.empty(max(int(lib.vqgnn_mp_num_chunks(nnz, MP_CHUNK)), 1), dtype=torch.int32, device=x.device)
+    _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(rowptr), n, nnz, MP_CHUNK, _lib.ptr(chunks), st))
     _lib.check(lib.vqgnn_mp_fwd(
-        _lib.ptr(rowptr.to(torch.int32)), _lib.ptr(col.to(torch.int32)), _lib.ptr(val.float().contiguous()), None,
+        _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), None, _lib.ptr(chunks), MP_CHUNK, nnz,
         n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, 1.0, 1.0,
         _lib.ptr(y), y.stride(0), None, 0, None, None, st))
     return y
