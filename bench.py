@@ -324,6 +324,9 @@ def main():
     l0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
+    cuprof = bool(os.environ.get("VQGNN_CUPROF"))   # ncu --profile-from-start off: capture the timed steps only
+    if cuprof:
+        torch.cuda.profiler.start()
     for i in range(args.steps):
         x, _, y = batches[i % len(batches)]
         flush_l2()
@@ -331,6 +334,8 @@ def main():
         train_step(model, opt, x, plans[i % len(plans)], y, distributed)
         ev[i][1].record()
     sync_all()
+    if cuprof:
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - l0 - args.steps   # minus the flush launches
     clocks = sampler.stop()
     t_ms = sum(a.elapsed_time(b) for a, b in ev)

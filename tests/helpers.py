@@ -77,3 +77,48 @@ def state_mismatches(sd_cuda, sd_oracle, tol):
         if not err < tol:
             bad.append((k, err))
     return bad, n_codes
+
+
+# ---- golden fixtures (tests/golden/*.npz, written by oracle/gen_golden.py) -----------------------
+def pack_batch(batch_A):
+    """Flatten a v1 / v2 `batch_A` tuple into named tensors."""
+    rec = {}
+    if len(batch_A) == 3:
+        batch_idx, subset, adj = batch_A
+        row, col, val = adj.coo()
+        rec.update({"bA.batch_idx": batch_idx, "bA.subset": subset, "bA.row": row, "bA.col": col,
+                    "bA.val": val, "bA.dim": torch.tensor(adj.sparse_sizes()[0])})
+    else:
+        deg_inv, A_BN, A_BB, A_NB_v, batch_idx = batch_A
+        rec.update({"bA.deg_inv": deg_inv, "bA.batch_idx": batch_idx})
+        for n, t in zip("rcv", A_BN):
+            rec["bA.A_BN." + n] = t
+        if A_BB is not None:
+            for n, t in zip("rcv", A_BB):
+                rec["bA.A_BB." + n] = t
+        if A_NB_v is not None:
+            rec["bA.A_NB_v"] = A_NB_v
+    return rec
+
+
+def unpack_batch(z):
+    t = lambda k: torch.from_numpy(z[k])
+    if "bA.subset" in z:
+        dim = int(z["bA.dim"])
+        return t("bA.batch_idx"), t("bA.subset"), CSRAdj.from_coo(t("bA.row"), t("bA.col"), t("bA.val"), (dim, dim))
+    A_BN = tuple(t("bA.A_BN." + n) for n in "rcv")
+    A_BB = tuple(t("bA.A_BB." + n) for n in "rcv") if "bA.A_BB.r" in z else None
+    A_NB_v = t("bA.A_NB_v") if "bA.A_NB_v" in z else None
+    return t("bA.deg_inv"), A_BN, A_BB, A_NB_v, t("bA.batch_idx")
+
+
+def load_golden(name):
+    import os
+
+    import numpy as np
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    return np.load(path, allow_pickle=False)
+
+
+def golden_sd(z, prefix):
+    return {k[len(prefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix)}
