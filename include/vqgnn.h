@@ -149,6 +149,48 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Message passing, GAT, v2 ("B+B'") formulation: OurGATConv.forward/message (vq_gnn_v2/convs.py:165-266)
+ * with vq_softmax == un-normalised exp (vq_gnn_v2/utils/vq_softmax.py:41-57), fused with the codeword
+ * gather, the ones-column denominator and the batch-row normalisation of vq_gnn_v2/models.py:161-198.
+ * Nodes of the batch graph: n < B batch rows (features x[n]), n >= B out-of-batch nodes (features = their
+ * codewords O_k[code, :D]); every node carries an implicit extra column of ones (models.py:176-177).
+ * att_l / att_r: [C+1] floats (the reference's [1,1,C+1] parameters).
+ * ------------------------------------------------------------------------------------------- */
+
+/* a_l[n] = <Xin[n], att_l>, a_r[n] = <Xin[n], att_r> for n < R (convs.py:188-190);
+ * stat[0] = max_n a_l[n], stat[1] = max_n a_r[n] ("Trick 1" scale, convs.py:209-211). */
+int vqgnn_gat_scores(int64_t R, int64_t B, const float* x, int64_t ldx, const int32_t* tail_node,
+                     const int16_t* codes, const float* O, int nb, int M, int D, int Wp, const float* att_l,
+                     const float* att_r, float* a_l, float* a_r, float* stat, void* stream);
+
+/* sigma = sqrt(stat[0]^2+1) sqrt(stat[1]^2+1); w_ij = val * exp(leaky_relu((a_l[j]+a_r[i])/sigma, slope));
+ * rows i < B:  den[i] = sum_j w_ij ; y[i, :C] = sum_j w_ij Xin[j, :C] / (den[i] + 1e-16)
+ * rows i >= B: info += <sum_j w_ij Xin[j, :C], O_k[code(node(i-B)), D:2D]>   (un-normalised, models.py:198)
+ * *info = info_scale * info.  Partition arguments as in vqgnn_mp_fwd. */
+int vqgnn_gat_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* chunk_row,
+                  int chunk, int64_t nnz, int64_t R, int64_t B, const float* x, int64_t ldx,
+                  const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M, int D, int Wp,
+                  const float* a_l, const float* a_r, const float* stat, float negative_slope,
+                  float info_scale, float* y, int64_t ldy, float* den, float* info, void* ws, void* stream);
+
+/* Backward of vqgnn_gat_scores + vqgnn_gat_fwd given dout = d loss / d y [B, C] and dinfo (device scalar or
+ * NULL = 1); `out` is the forward's y.  Outputs:
+ *   dyn [B, C]  = dout / (den + 1e-16): the gradient w.r.t. the un-normalised conv output, which is what the
+ *                 reference's VQ hook receives (vq_gnn_v2/models.py:181-185);
+ *   dx  [B, C]  (may be NULL), datt_l / datt_r [C+1];
+ * scratch: dden [B], ds_l / ds_r [R].  Includes the gradient through the max-based scale (convs.py:209, in
+ * the autograd graph) and of info_backward (tail rows weigh tail_scale * dinfo * gradient codeword). */
+int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* chunk_row,
+                  int64_t nnz, int64_t R, const int32_t* browptr, const int32_t* brow, const float* bval,
+                  const int32_t* bchunk_row, int64_t bnnz, int chunk, int64_t B, const float* x, int64_t ldx,
+                  const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M, int D, int Wp,
+                  const float* att_l, const float* att_r, const float* a_l, const float* a_r, const float* stat,
+                  float negative_slope, const float* out, int64_t ldo, const float* den, const float* dout,
+                  int64_t lddo, float tail_scale, const float* dinfo, float* dyn, int64_t lddyn, float* dden,
+                  float* ds_l, float* ds_r, float* dx, int64_t lddx, float* datt_l, float* datt_r,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * helpers
  * ------------------------------------------------------------------------------------------- */
 int vqgnn_fill_zero(void* ptr, size_t bytes, void* stream);

@@ -53,6 +53,18 @@ def rel_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+def att_grad_err(got: dict, want: dict):
+    """Error of the GAT attention-vector gradients, relative to their JOINT scale.  "Trick 1" (convs.py:209-211)
+    makes the scores invariant to a rescaling of att_l (att_r) when max|a_l| >> 1, so the gradient along
+    att_l is a difference of large terms: in fp32 the reference itself moves by ~1e-3 of |d att_l| between
+    CPU and GPU (scratch/dbg_gat.py), while it is stable to ~1e-6 of the joint (att_l, att_r) gradient."""
+    keys = [k for k in want if "att_" in k and k in got]
+    if not keys:
+        return 0.0
+    scale = max(float(want[k].abs().max()) for k in keys) + 1e-30
+    return max(float((got[k].detach().double().cpu() - want[k].detach().double().cpu()).abs().max()) for k in keys) / scale
+
+
 def loss_weights(shape):
     """Per-element random loss weights: the gradient must VARY across batch rows, otherwise the
     gradient BatchNorm (eps = 1e-24, vq.py:87) divides rounding noise by 1e-12."""

@@ -13,192 +13,9 @@
 //
 // Reference maths: vq_gnn_v2/models.py:161-198, vq_gnn_v2/convs.py:65-101,
 // vq_gnn_v1/models.py:170-223 + vq_gnn_v1/utils/dataloader.py:144-192.
-#include "common.cuh"
+#include "mp_common.cuh"
 
 namespace vqgnn {
-
-constexpr int kMpWarps = 8;
-constexpr int kMpUnroll = 4;
-
-struct Codebook {
-  const int32_t* tail_node;  // [T] or nullptr (identity)
-  const int16_t* codes;      // [N, nb]
-  const float* O;            // [nb, M, Wp]
-  int nb, M, D, Wp;
-};
-
-template <int VEC>
-__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VEC]) {
-  if constexpr (VEC == 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-  } else {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) v[i] = __ldg(p + i);
-  }
-}
-template <int VEC>
-__device__ __forceinline__ void st_vec(float* p, const float (&v)[VEC]) {
-  if constexpr (VEC == 4) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) p[i] = v[i];
-  }
-}
-template <int VEC>
-__device__ __forceinline__ void red_vec(float* p, const float (&v)[VEC]) {
-  if constexpr (VEC == 4) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                 "f"(v[3])
-                 : "memory");
-  } else {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) atomicAdd(p + i, v[i]);
-  }
-}
-// one 32 B sector: feature half -> a, gradient half -> b (Wp == 8, D == 4)
-__device__ __forceinline__ void ld_sector(const float* p, float (&a)[4], float (&b)[4]) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3])
-               : "l"(p));
-}
-
-// Walks one chunk [eb, ee) of the CSR for the lane's VEC columns starting at c0 (branch k, offset off) and
-// calls flush(row, acc, gqa, whole) at every row end inside the chunk and once for a trailing partial row
-// (whole = the row starts and ends inside this chunk, so no other warp touches its output).
-//   acc += val * (src < B ? dense[src, c0..] : tscale * O_k[code, half_off + off ..])
-//   gqa += rval * O_k[code, D + off ..]                                  (HAS_GQ, tail entries only)
-// WIDE: VEC == 4, HAS_GQ, Wp == 8, D == 4, half_off == 0 -> one 256-bit load per gathered codeword.
-template <int VEC, bool HAS_GQ, bool WIDE, class Flush>
-__device__ __forceinline__ void walk_chunk(int eb, int ee, int r, int64_t R,
-                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                           const float* __restrict__ val, const float* __restrict__ rval, int B,
-                                           const float* __restrict__ dense, int64_t ldd, const Codebook& cb,
-                                           int half_off, float tscale, bool active, int c0, int k, int off,
-                                           int lane, Flush&& flush) {
-  constexpr int U = kMpUnroll;
-  float acc[VEC], gqa[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
-  // row boundaries: lane i holds rowptr[rbase + i]; row r is [shfl(r - rbase), shfl(r - rbase + 1))
-  int rbase = r;
-  int rp_l = __ldg(rowptr + min(static_cast<int64_t>(rbase) + lane, R));
-  int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
-  bool pending = false;
-
-  for (int bb = eb; bb < ee; bb += 32) {
-    const int e = bb + lane;
-    int c_l = -1, node_l = 0;
-    float v_l = 0.f, rv_l = 0.f;
-    if (e < ee) {
-      c_l = __ldg(col + e);
-      v_l = __ldg(val + e);
-      if (HAS_GQ) rv_l = __ldg(rval + e);
-      if (c_l >= B) node_l = cb.tail_node ? __ldg(cb.tail_node + (c_l - B)) : (c_l - B);
-    }
-    const int cnt = min(32, ee - bb);
-    int j = 0;
-    while (j < cnt) {
-      const int jend = min(cnt, re - bb);  // entries of row r inside this batch end here
-      for (; j < jend; j += U) {
-        int c[U], node[U];
-        float v[U], rv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int src_lane = min(j + u, 31);
-          c[u] = __shfl_sync(0xffffffffu, c_l, src_lane);
-          v[u] = __shfl_sync(0xffffffffu, v_l, src_lane);
-          node[u] = __shfl_sync(0xffffffffu, node_l, src_lane);
-          rv[u] = HAS_GQ ? __shfl_sync(0xffffffffu, rv_l, src_lane) : 0.f;
-          if (j + u >= jend) c[u] = -1;
-        }
-        if (!active) continue;
-        const float* p[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {  // first level: code loads for tail entries (independent)
-          p[u] = nullptr;
-          if (c[u] >= B) {
-            const int code = __ldg(cb.codes + static_cast<int64_t>(node[u]) * cb.nb + k);
-            p[u] = cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + off;
-          } else if (c[u] >= 0) {
-            p[u] = dense + static_cast<int64_t>(c[u]) * ldd + c0;
-          }
-        }
-        float a[U][VEC], g[U][VEC];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {  // second level: the gathers
-          if (c[u] >= B) {
-            if constexpr (WIDE) {
-              ld_sector(p[u], a[u], g[u]);
-            } else {
-              ld_vec<VEC>(p[u] + half_off, a[u]);
-              if (HAS_GQ) ld_vec<VEC>(p[u] + cb.D, g[u]);
-            }
-          } else if (c[u] >= 0) {
-            ld_vec<VEC>(p[u], a[u]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (c[u] >= B) {
-            const float s = v[u] * tscale;
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s, a[u][i], acc[i]);
-            if (HAS_GQ) {
-#pragma unroll
-              for (int i = 0; i < VEC; ++i) gqa[i] = fmaf(rv[u], g[u][i], gqa[i]);
-            }
-          } else if (c[u] >= 0) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(v[u], a[u][i], acc[i]);
-          }
-        }
-      }
-      j = jend;
-      pending = true;
-      if (bb + j == re) {  // row r is complete
-        flush(r, acc, gqa, rs >= eb);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
-        pending = false;
-        if (bb + j >= ee) break;
-        do {  // next non-empty row (empty rows keep the pre-initialised output)
-          ++r;
-          if (r - rbase >= 31) {
-            rbase = r;
-            rp_l = __ldg(rowptr + min(static_cast<int64_t>(rbase) + lane, R));
-          }
-          rs = __shfl_sync(0xffffffffu, rp_l, r - rbase);
-          re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
-        } while (re <= bb + j);
-      }
-    }
-  }
-  if (pending) flush(r, acc, gqa, false);
-}
-
-// block-level fp64 reduction of the info partials + "last block finishes" epilogue
-__device__ __forceinline__ void info_reduce(double part, double* ws_sum, unsigned int* ws_count,
-                                            float info_scale, float* info) {
-  __shared__ double sh[kMpWarps];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  part = warp_sum(part);
-  if (lane == 0) sh[warp] = part;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0.0;
-#pragma unroll
-    for (int i = 0; i < kMpWarps; ++i) t += sh[i];
-    atomicAdd(ws_sum, t);
-    __threadfence();
-    const unsigned int ticket = atomicAdd(ws_count, 1u);
-    if (ticket == gridDim.x - 1) {
-      const double total = atomicAdd(ws_sum, 0.0);
-      *info = static_cast<float>(static_cast<double>(info_scale) * total);
-    }
-  }
-}
 
 // chunk c starts at entry c*chunk; chunk_row[c] = the row that entry belongs to
 __global__ void mp_chunk_rows_kernel(const int32_t* __restrict__ rowptr, int64_t R, int64_t nnz, int chunk,
@@ -223,51 +40,52 @@ __global__ void __launch_bounds__(kMpWarps * 32)
                   const float* __restrict__ x, int64_t ldx, Codebook cb, int C, int nslab, float feat_scale,
                   float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ gq, int64_t ldgq,
                   float* __restrict__ info, double* ws_sum, unsigned int* ws_count) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
-  double part = 0.0;
-  if (task < static_cast<int64_t>(n_chunks) * nslab) {
-    // slab-major order: the warps of a CTA share a slab (same codebook branches -> L1/L2 locality)
-    const int slab = static_cast<int>(task / n_chunks);
-    const int ch = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
-    const int c0 = (slab * 32 + lane) * VEC;
-    const bool active = c0 < C;
-    const int k = active ? c0 / cb.D : 0, off = active ? c0 - k * cb.D : 0;
-    const int eb = ch * chunk, ee = min(eb + chunk, nnz);
-    float fpart = 0.f;
-    auto flush = [&](int r, float (&acc)[VEC], float (&gqa)[VEC], bool whole) {
-      if (!active) return;
-      if (r < B) {
-        float* yp = y + static_cast<int64_t>(r) * ldy + c0;
-        if (whole) st_vec<VEC>(yp, acc);
-        else red_vec<VEC>(yp, acc);
-        if (HAS_GQ) {
-          if (gq) {
-            float* gp = gq + static_cast<int64_t>(r) * ldgq + c0;
-            if (whole) st_vec<VEC>(gp, gqa);
-            else red_vec<VEC>(gp, gqa);
-          }
-          if (info) {  // v1: <x[r], gq[r]>  (vq_gnn_v1/models.py:223 rewritten row-wise)
-            float xr[VEC];
-            ld_vec<VEC>(x + static_cast<int64_t>(r) * ldx + c0, xr);
+  const int lane = threadIdx.x & 31;
+  const MpTask t = mp_task<VEC>(chunk_row, n_chunks, chunk, nnz, nslab, C, cb.D);
+  float fpart = 0.f;
+  if (t.valid) {
+    const int c0 = t.c0, k = t.k, off = t.off;
+    float acc[VEC], gqa[VEC];
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) fpart = fmaf(xr[i], gqa[i], fpart);
-          }
-        }
-      } else if (info) {  // v2: <Y[r], Gq[r]> with Gq the node's own gradient codeword (models.py:198)
-        const int node = cb.tail_node ? __ldg(cb.tail_node + (r - B)) : (r - B);
-        const int code = __ldg(cb.codes + static_cast<int64_t>(node) * cb.nb + k);
-        float gv[VEC];
-        ld_vec<VEC>(cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + cb.D + off, gv);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) fpart = fmaf(acc[i], gv[i], fpart);
-      }
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
+    auto body = [&](const EntryGroup& g) {
+      if (t.active) gather_accumulate<VEC, HAS_GQ, WIDE>(g, B, x, ldx, cb, 0, feat_scale, c0, k, off, acc, gqa);
     };
-    walk_chunk<VEC, HAS_GQ, WIDE>(eb, ee, __ldg(chunk_row + ch), R, rowptr, col, val, rval, B, x, ldx, cb, 0,
-                                  feat_scale, active, c0, k, off, lane, flush);
-    part = static_cast<double>(fpart);
+    auto flush = [&](int r, bool whole) {
+      if (t.active) {
+        if (r < B) {
+          float* yp = y + static_cast<int64_t>(r) * ldy + c0;
+          if (whole) st_vec<VEC>(yp, acc);
+          else red_vec<VEC>(yp, acc);
+          if (HAS_GQ) {
+            if (gq) {
+              float* gp = gq + static_cast<int64_t>(r) * ldgq + c0;
+              if (whole) st_vec<VEC>(gp, gqa);
+              else red_vec<VEC>(gp, gqa);
+            }
+            if (info) {  // v1: <x[r], gq[r]>  (vq_gnn_v1/models.py:223 rewritten row-wise)
+              float xr[VEC];
+              ld_vec<VEC>(x + static_cast<int64_t>(r) * ldx + c0, xr);
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) fpart = fmaf(xr[i], gqa[i], fpart);
+            }
+          }
+        } else if (info) {  // v2: <Y[r], Gq[r]> with Gq the node's own gradient codeword (models.py:198)
+          const int node = cb.tail_node ? __ldg(cb.tail_node + (r - B)) : (r - B);
+          const int code = __ldg(cb.codes + static_cast<int64_t>(node) * cb.nb + k);
+          float gv[VEC];
+          ld_vec<VEC>(cb.O + (static_cast<int64_t>(k) * cb.M + code) * cb.Wp + cb.D + off, gv);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) fpart = fmaf(acc[i], gv[i], fpart);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
+    };
+    PlainWeights pol;
+    walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body, flush);
   }
-  if (info) info_reduce(part, ws_sum, ws_count, info_scale, info);
+  if (info) info_reduce(static_cast<double>(fpart), ws_sum, ws_count, info_scale, info);
 }
 
 // dx <- gq_scale * dinfo * gq  (or 0): the part of the backward that does not depend on the CSR
@@ -300,33 +118,24 @@ __global__ void __launch_bounds__(kMpWarps * 32)
                   const float* __restrict__ bval, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
                   int nnz, int B, const float* __restrict__ dy, int64_t lddy, Codebook cb, int C, int nslab,
                   float tail_scale, const float* __restrict__ dinfo, float* __restrict__ dx, int64_t lddx) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
-  if (task >= static_cast<int64_t>(n_chunks) * nslab) return;
-  const int slab = static_cast<int>(task / n_chunks);
-  const int ch = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
-  const int c0 = (slab * 32 + lane) * VEC;
-  const bool active = c0 < C;
-  const int k = active ? c0 / cb.D : 0, off = active ? c0 - k * cb.D : 0;
-  const float di = dinfo ? __ldg(dinfo) : 1.f;
-  const int eb = ch * chunk, ee = min(eb + chunk, nnz);
-  auto flush = [&](int j, float (&acc)[VEC], float (&)[VEC], bool) {
-    if (active) red_vec<VEC>(dx + static_cast<int64_t>(j) * lddx + c0, acc);  // onto the initialised dx
+  const int lane = threadIdx.x & 31;
+  const MpTask t = mp_task<VEC>(chunk_row, n_chunks, chunk, nnz, nslab, C, cb.D);
+  if (!t.valid) return;
+  const float ts = tail_scale * (dinfo ? __ldg(dinfo) : 1.f);
+  float acc[VEC], unused[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f, unused[i] = 0.f;
+  auto body = [&](const EntryGroup& g) {
+    if (t.active)
+      gather_accumulate<VEC, false, false>(g, B, dy, lddy, cb, cb.D, ts, t.c0, t.k, t.off, acc, unused);
   };
-  walk_chunk<VEC, false, false>(eb, ee, __ldg(chunk_row + ch), B, browptr, brow, bval, nullptr, B, dy, lddy, cb,
-                                cb.D, tail_scale * di, active, c0, k, off, lane, flush);
-}
-
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
-
-static int zero_rows(float* p, int64_t rows, int C, int64_t ld, cudaStream_t s) {
-  if (ld == C) {
-    VQ_CUDA(cudaMemsetAsync(p, 0, sizeof(float) * rows * C, s));
-  } else {
-    VQ_CUDA(cudaMemset2DAsync(p, sizeof(float) * ld, 0, sizeof(float) * C, rows, s));
-  }
-  return VQGNN_OK;
+  auto flush = [&](int j, bool) {
+    if (t.active) red_vec<VEC>(dx + static_cast<int64_t>(j) * lddx + t.c0, acc);  // onto the initialised dx
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  };
+  PlainWeights pol;
+  walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body, flush);
 }
 
 }  // namespace vqgnn

@@ -1,0 +1,91 @@
+"""GAT message passing of the VQ layers (v2 "B+B'" formulation) as one autograd Function over libvqgnn.
+
+Reference: `LowRankGNNLayer.forward` with `OurGATConv` (vq_gnn_v2/models.py:161-198, vq_gnn_v2/convs.py:165-266,
+vq_gnn_v2/utils/vq_softmax.py:41-57).  The reference concatenates a ones column, runs PyG's per-edge
+`message` (materialising nnz x (C+1) messages) and divides by the aggregated ones column afterwards; here
+the codeword gather, the edge weights, the denominator and the normalisation are fused into
+`vqgnn_gat_scores` + `vqgnn_gat_fwd`, and the whole backward (including the gradient through the max-based
+"Trick 1" scale, which the reference leaves inside the autograd graph) is `vqgnn_gat_bwd`.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .graph import MP_CHUNK, BatchPlan
+
+Tensor = torch.Tensor
+
+
+class VQGATFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, att_l: Tensor, att_r: Tensor, layer, plan: BatchPlan, wu: float,
+                fire_hook: bool, slope: float):
+        _lib.require_device(x)
+        lib, st = _lib.load(), _lib.stream()
+        bank = layer.bank
+        B, C = x.shape
+        R, dev = plan.R, x.device
+        al, ar = att_l.detach().reshape(-1).contiguous(), att_r.detach().reshape(-1).contiguous()
+        assert al.numel() == C + 1 and ar.numel() == C + 1
+        a_l, a_r = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        stat = torch.empty(2, device=dev)
+        _lib.check(lib.vqgnn_gat_scores(
+            R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O),
+            bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r),
+            _lib.ptr(stat), st))
+        y = torch.empty(B, C, device=dev)
+        den = torch.empty(B, device=dev)
+        need_info = plan.training
+        info = torch.zeros((), device=dev)
+        ws = torch.empty(8, dtype=torch.float64, device=dev) if need_info else None
+        _lib.check(lib.vqgnn_gat_fwd(
+            _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
+            _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, R, B, _lib.ptr(x), x.stride(0),
+            _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
+            _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), float(slope), float(wu), _lib.ptr(y), y.stride(0),
+            _lib.ptr(den), _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+        ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook, ctx.slope = layer, plan, float(wu), fire_hook, float(slope)
+        ctx.att_shape = att_l.shape
+        ctx.save_for_backward(x, al, ar, a_l, a_r, stat, y, den)
+        return y, info
+
+    @staticmethod
+    def backward(ctx, dy: Tensor, dinfo: Tensor):
+        x, al, ar, a_l, a_r, stat, y, den = ctx.saved_tensors
+        layer, plan, wu = ctx.layer, ctx.plan, ctx.wu
+        lib, st = _lib.load(), _lib.stream()
+        bank = layer.bank
+        B, C = x.shape
+        R, dev = plan.R, x.device
+        dy = dy.contiguous().float()
+        dinfo = dinfo.contiguous().float()
+        dyn = torch.empty(B, C, device=dev)
+        dden = torch.empty(B, device=dev)
+        ds_l, ds_r = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        datt_l, datt_r = torch.empty(C + 1, device=dev), torch.empty(C + 1, device=dev)
+        dx = torch.empty(B, C, device=dev) if ctx.needs_input_grad[0] else None
+        _lib.check(lib.vqgnn_gat_bwd(
+            _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
+            _lib.ptr(plan.chunk_rows('fwd')), plan.nnz, R,
+            _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
+            _lib.ptr(plan.chunk_rows('bwd')), int(plan.bwd_col.numel()), MP_CHUNK, B, _lib.ptr(x), x.stride(0),
+            _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
+            _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), ctx.slope,
+            _lib.ptr(y), y.stride(0), _lib.ptr(den), _lib.ptr(dy), dy.stride(0), wu, _lib.ptr(dinfo),
+            _lib.ptr(dyn), dyn.stride(0), _lib.ptr(dden), _lib.ptr(ds_l), _lib.ptr(ds_r),
+            _lib.ptr(dx), dx.stride(0) if dx is not None else 0, _lib.ptr(datt_l), _lib.ptr(datt_r), st))
+        if ctx.fire_hook:
+            # the hook sees d loss / d (un-normalised conv output)[:B, :C]  (vq_gnn_v2/models.py:181-185)
+            bank.run(x, dyn, plan.batch_idx, True)
+        return dx, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), None, None, None, None, None
+
+
+def gat_conv(layer, x: Tensor, plan: BatchPlan, wu: float, fire_hook: bool):
+    """-> (y [B, C] normalised batch rows, info_backward scalar)."""
+    if plan.version != 'v2':
+        raise NotImplementedError("GAT is implemented for the v2 (B+B') formulation; the v1 per-branch "
+                                  "(B+M, D+1 columns, add_flag quantiser) GAT is the next row (DESIGN.md)")
+    conv = layer.conv
+    return VQGATFunction.apply(x, conv.att_l, conv.att_r, layer, plan, float(wu), fire_hook,
+                               float(conv.negative_slope))
