@@ -88,11 +88,16 @@ int vqgnn_vq_whiten(const double* sums, double count, const double* d_count, int
  * (models.py:46,63; codes_ld = row stride of the code table, so a sub-range of branches can be updated); if stats != NULL adds z to stats[k, code, :W] and 1 to stats[k, code, Wp]
  * (the one-hot^T @ z GEMM and column sum of vq.py:243,256 as a segmented sum).  `stats` must be zeroed
  * by the caller (vqgnn_fill_zero).  g == NULL selects the feature-only form (feature_update, W = D).
- * impl: 0 = exact-fp32 SIMT kernel (parity anchor), 1 = tcgen05/TMEM 3xTF32 kernel (D == 4 only). */
+ * impl: 0 = exact-fp32 SIMT kernel (parity anchor; ws unused, may be NULL);
+ *       1 = tcgen05 / TMEM kernel (kind::tf32, error-compensated 3xTF32, TMA-fed codebook tiles, fused
+ *           argmin epilogue; packed width D+Dg in {4, 8, 9}); needs ws of vqgnn_vq_assign_workspace_bytes()
+ *           bytes (the codebook re-packed into MMA tiles), 16 B aligned.  Codes may differ from impl 0 only
+ *           at near-ties of the fp32 distances. */
+size_t vqgnn_vq_assign_workspace_bytes(int nb, int M);
 int vqgnn_vq_assign(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
                     const float* shift, const float* E, int64_t B, int nb, int M, int D, int Dg, int Wp,
                     const int32_t* batch_idx, int16_t* codes, int64_t codes_ld, int16_t* idx, float* stats,
-                    int impl, void* stream);
+                    int impl, void* ws, size_t ws_bytes, void* stream);
 
 /* EMA + Laplace smoothing + codeword recovery (vq.py:177-200 / 242-275), one CTA per branch:
  *   size <- decay*size + (1-decay)*count; if warm_up: size <- (size+1e-5)/(sum(size)+M*1e-5)*sum(size);

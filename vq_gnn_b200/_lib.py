@@ -28,8 +28,9 @@ _SIGNATURES = {
     "vqgnn_vq_moments": (C.c_int, [vp, i64, vp, i64, i64, i32, i32, vp, vp]),
     "vqgnn_vq_whiten": (C.c_int, [vp, f64, vp, i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32,
                                   i32, i32, vp, vp, vp, vp, vp]),
+    "vqgnn_vq_assign_workspace_bytes": (C.c_size_t, [i32, i32]),
     "vqgnn_vq_assign": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, i64, vp,
-                                  vp, i32, vp]),
+                                  vp, i32, vp, C.c_size_t, vp]),
     "vqgnn_vq_finalize": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, f64, i32, f32, f32, f32, vp, vp, vp, vp,
                                     vp, vp, vp, vp, vp, vp]),
     "vqgnn_mp_workspace_bytes": (C.c_size_t, []),
@@ -100,7 +101,7 @@ class _Proxy:
 
 
 _NO_STREAM = {"vqgnn_abi_version", "vqgnn_arch_check", "vqgnn_last_error", "vqgnn_launch_count",
-              "vqgnn_mp_workspace_bytes", "vqgnn_mp_num_chunks"}
+              "vqgnn_mp_workspace_bytes", "vqgnn_mp_num_chunks", "vqgnn_vq_assign_workspace_bytes"}
 
 
 def load():

@@ -320,10 +320,11 @@ extern "C" int vqgnn_vq_whiten(const double* sums, double count, const double* d
 }
 
 namespace vqgnn {
+size_t assign_tc_workspace_bytes(int nb, int M);
 int launch_assign_tc(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
                      const float* shift, const float* E, int64_t B, int nb, int M, int D, int Dg, int Wp,
                      const int32_t* batch_idx, int16_t* codes, int64_t codes_ld, int16_t* idx, float* stats,
-                     cudaStream_t s);
+                     void* ws, size_t ws_bytes, cudaStream_t s);
 
 template <int NV>
 static int launch_assign_simt(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
@@ -352,10 +353,12 @@ static int launch_assign_simt(const float* x, int64_t ldx, const float* g, int64
 }
 }  // namespace vqgnn
 
+extern "C" size_t vqgnn_vq_assign_workspace_bytes(int nb, int M) { return assign_tc_workspace_bytes(nb, M); }
+
 extern "C" int vqgnn_vq_assign(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
                                const float* shift, const float* E, int64_t B, int nb, int M, int D, int Dg,
                                int Wp, const int32_t* batch_idx, int16_t* codes, int64_t codes_ld, int16_t* idx,
-                               float* stats, int impl, void* stream) {
+                               float* stats, int impl, void* ws, size_t ws_bytes, void* stream) {
   VQ_CHECK_ARG(x && scale && shift && E && B > 0 && nb > 0 && M > 0 && D > 0, "vq_assign: bad arguments");
   VQ_CHECK_ARG(M <= 32767, "vq_assign: codes are int16, M must be <= 32767 (got %d)", M);
   VQ_CHECK_ARG(!codes || batch_idx, "vq_assign: codes scatter needs batch_idx");
@@ -363,7 +366,9 @@ extern "C" int vqgnn_vq_assign(const float* x, int64_t ldx, const float* g, int6
   VQ_CHECK_ARG(Wp % 4 == 0 && Wp >= D + (g ? Dg : 0), "vq_assign: Wp must be a multiple of 4 covering W");
   VQ_CHECK_ARG(nb <= 65535, "vq_assign: too many branches");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 1) return launch_assign_tc(x, ldx, g, ldg, scale, shift, E, B, nb, M, D, Dg, Wp, batch_idx, codes, codes_ld, idx, stats, s);
+  if (impl == 1)
+    return launch_assign_tc(x, ldx, g, ldg, scale, shift, E, B, nb, M, D, Dg, Wp, batch_idx, codes, codes_ld, idx,
+                            stats, ws, ws_bytes, s);
   const int w_use = D + (g ? Dg : 0);
   const int nv = (w_use + 3) / 4;
   switch (nv) {

@@ -132,10 +132,14 @@ class VQBank:
             assert batch_idx.dtype == torch.int32 and batch_idx.is_cuda
             bidx = batch_idx
             codes_ptr = _lib.C.c_void_p(self.codes.data_ptr() + 2 * k0)
+        ws, ws_bytes = None, 0
+        if self.assign_impl == 1:     # tcgen05 path: the codebook re-packed into MMA tiles
+            ws_bytes = int(lib.vqgnn_vq_assign_workspace_bytes(nbc, M))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.vqgnn_vq_assign(
             _lib.ptr(xk), xk.stride(0), _lib.ptr(gk), gk.stride(0) if joint else 0, _lib.ptr(scale),
             _lib.ptr(shift), _lib.ptr(E), B, nbc, M, D, Dg, Wp, _lib.ptr(bidx), codes_ptr, self.nb,
-            _lib.ptr(idx), _lib.ptr(stats), self.assign_impl, st))
+            _lib.ptr(idx), _lib.ptr(stats), self.assign_impl, _lib.ptr(ws), ws_bytes, st))
         if training:
             if self.distributed:
                 torch.distributed.all_reduce(stats, group=self.process_group)
