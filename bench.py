@@ -110,7 +110,8 @@ def build_workload(dev, rank: int, world: int, scale: float = 1.0, n_batches: in
     del row
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
     # rank r samples its seeds from its own contiguous node partition
-    lo, hi = rank * N // world, (rank + 1) * N // world
+    from vq_gnn_b200 import dist as vdist
+    lo, hi = vdist.partition_range(N, rank, world)
     seeds = lo + torch.randperm(hi - lo, generator=gen, device=dev)[:c["B"]]
     node_lists = sampling.cont_sampler(g, seeds, c["walk"], c["B"], generator=gen)[:n_batches]
     batches = []
@@ -158,14 +159,8 @@ def train_step(model, opt, x, batch_A, y, distributed: bool):
     loss = F.cross_entropy(out, y) + info
     loss.backward()
     if distributed:
-        grads = [p.grad for p in model.parameters() if p.grad is not None]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        torch.distributed.all_reduce(flat)
-        flat /= torch.distributed.get_world_size()
-        off = 0
-        for g in grads:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        from vq_gnn_b200 import dist as vdist
+        vdist.allreduce_mean_grads_(model.parameters())
     opt.step()
     return loss
 
@@ -293,7 +288,8 @@ def main():
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=dev)
+        import datetime
+        torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     _lib.require_device(torch.zeros(1, device=dev))
     pk = peaks()
 
@@ -349,6 +345,11 @@ def main():
     ms_per_step = t_ms / args.steps
     value = float(nodes.item()) * c["layers"] / (t_ms / 1e3)
     model.check_status()
+    replica_div = None
+    if distributed:   # codebook replicas must stay identical across ranks
+        from vq_gnn_b200 import dist as vdist
+        replica_div = max(max(vdist.replicas_max_abs_diff(l.bank.E), vdist.replicas_max_abs_diff(l.bank.size))
+                          for l in model.convs)
 
     # ---- end-to-end through the public API from pinned host buffers ----------------------------
     host = []
@@ -397,7 +398,7 @@ def main():
 
     # ---- attribution pass: CUDA events around every C-ABI launch (dominant kernel + roofline) ---
     roofline, kernel_table = None, {}
-    if rank == 0:
+    if True:   # every rank runs the pass (its steps contain collectives); rank 0 reports
         _lib.PROFILER.enabled = True
         _lib.PROFILER.reset()
         n_attr = min(args.steps, 8)
@@ -454,7 +455,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "nodes/s/layer", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "kernels": kernel_table, "assign_impl": "tcgen05" if args.assign_impl == 1 else "simt-fp32"}
+                "replica_max_abs_diff": replica_div, "kernels": kernel_table, "assign_impl": "tcgen05" if args.assign_impl == 1 else "simt-fp32"}
         print(json.dumps(line), flush=True)
     if distributed:
         torch.distributed.barrier()

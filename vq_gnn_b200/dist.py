@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing (one process per GPU, `torch.distributed`; NCCL on the GPUs, gloo in the CPU tests).
+
+The reference has no distributed code; the design is SURVEY.md §8e:
+  * every rank owns a contiguous node range (`partition_range`) and samples its mini-batch from it,
+  * every rank holds a replica of each layer's codebooks and code table,
+  * the ONLY exchanges are sums: the whitening moments and the per-codeword statistics inside the VQ update
+    (`allreduce_sum_`, called by `VQBank.run` between its kernels) and the dense weight gradients once per
+    step (`allreduce_mean_grads_`).  Counts are integers held in fp32/fp64 (< 2^24): the reduced histogram is
+    bit-exact for any reduction order, which is what keeps the replicas identical.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+Tensor = torch.Tensor
+
+
+def world(group=None) -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def partition_range(N: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous node range [lo, hi) owned by `rank` (ranges tile [0, N) without overlap)."""
+    return rank * N // world_size, (rank + 1) * N // world_size
+
+
+def allreduce_sum_(t: Tensor, group=None) -> Tensor:
+    """In-place sum over ranks; a no-op for a single process."""
+    if world(group)[1] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def allreduce_mean_grads_(params: Iterable[Tensor], group=None) -> None:
+    """One flat allreduce of every available `.grad`, averaged over ranks (data parallel)."""
+    ws = world(group)[1]
+    if ws == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= ws
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+
+
+def replicas_max_abs_diff(t: Tensor, group=None) -> float:
+    """max |t_rank - t_rank0| over ranks (0.0 for identical replicas): a cheap divergence check."""
+    if world(group)[1] == 1:
+        return 0.0
+    ref = t.detach().clone()
+    dist.broadcast(ref, src=0, group=group)
+    d = (t.detach() - ref).abs().max().reshape(1).float()
+    dist.all_reduce(d, op=dist.ReduceOp.MAX, group=group)
+    return float(d.item())

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, dist
 
 Tensor = torch.Tensor
 
@@ -111,7 +111,7 @@ class VQBank:
                                             gk.stride(0) if joint else 0, B, C, Cg, _lib.ptr(sums), st))
             if self.distributed:   # global batch statistics: every rank whitens identically
                 sums[-1] = float(B)
-                torch.distributed.all_reduce(sums, group=self.process_group)
+                dist.allreduce_sum_(sums, self.process_group)
                 d_count = sums[-1:]
         seed = 1 if (joint and training and not self.bn_inited) else 0
         _lib.check(lib.vqgnn_vq_whiten(
@@ -142,7 +142,7 @@ class VQBank:
             _lib.ptr(idx), _lib.ptr(stats), self.assign_impl, _lib.ptr(ws), ws_bytes, st))
         if training:
             if self.distributed:
-                torch.distributed.all_reduce(stats, group=self.process_group)
+                dist.allreduce_sum_(stats, self.process_group)
             _lib.check(lib.vqgnn_vq_finalize(
                 _lib.ptr(stats), nbc, M, D, Dg, Wp, 1 if joint else 0, float(self.decay),
                 1 if self.warm_up_flag else 0, self.eps, self.scale[0], self.scale[1], _lib.ptr(rm_f),
