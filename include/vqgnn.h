@@ -153,6 +153,26 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
                  const float* gq, int64_t ldgq, float gq_scale, const float* dinfo, float* dx, int64_t lddx,
                  void* stream);
 
+/* Out-of-batch ("tail") part of the forward with the codebooks of a branch group resident in shared
+ * memory (csrc/mp_tail.cu) -- the fast path for the v1 formulation, where every batch row has hundreds of
+ * out-of-batch neighbours (vq_gnn_v1/utils/dataloader.py:149-154 + vq_gnn_v1/models.py:181-223).
+ *   vqgnn_mp_tail_group(M, D, Wp): branches per group G (8 or 6), or 0 if the shape is not supported
+ *                                  (needs D == 4, Wp == 8, G*M*32 B <= 192 KB).
+ *   vqgnn_codes_group: codes_g[(k/G)*N + node][k%G] = codes[node, k]  (codes_g: [ceil(nb/G)][N][8] int16) for
+ *                      the listed nodes (rows == NULL: all N) -- the group-major mirror of the code table.
+ *   vqgnn_mp_fwd_tail: over a CSR holding ONLY tail entries (node = global node id):
+ *       y[r]  += sum_e val[e] * feat_scale * O_k[code_k(node[e]), :D]      (y, gq accumulate: run it AFTER
+ *       gq[r] += sum_e rval[e] * O_k[code_k(node[e]), D:2D]                 vqgnn_mp_fwd on the in-batch part)
+ *       *info += info_scale * sum_r <x[r], gq contribution>               (info must be zero-initialised) */
+int vqgnn_mp_tail_group(int M, int D, int Wp);
+int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* rows, int64_t n_rows, int64_t N, int G,
+                      int16_t* codes_g, void* stream);
+int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* val, const float* rval,
+                      const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* x, int64_t ldx,
+                      const int16_t* codes_g, int64_t N, const float* O, int nb, int M, int D, int Wp,
+                      float feat_scale, float info_scale, float* y, int64_t ldy, float* gq, int64_t ldgq,
+                      float* info, void* ws, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Message passing, GAT, v2 ("B+B'") formulation: OurGATConv.forward/message (vq_gnn_v2/convs.py:165-266)
  * with vq_softmax == un-normalised exp (vq_gnn_v2/utils/vq_softmax.py:41-57), fused with the codeword

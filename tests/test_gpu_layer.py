@@ -206,3 +206,31 @@ def test_hub_rows_cut_by_chunk_boundaries(version, conv):
     layer = layer.to(dev)
     x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
     _compare(_run_cuda(layer, batch_A, x, 3, dev), _run_oracle(o, batch_A, x, 3), layer, o)
+
+
+@pytest.mark.parametrize("conv,C,M,B,E", [("SAGE", 8, 16, 120, 2000), ("GCN", 8, 16, 120, 2000),
+                                          ("SAGE", 28, 1024, 200, 6000), ("SAGE", 132, 64, 150, 40000),
+                                          ("GCN", 24, 512, 64, 30000)])
+def test_v1_shared_memory_tail_kernel(conv, C, M, B, E):
+    """The shared-memory codebook kernel (csrc/mp_tail.cu) forced on small graphs: short and empty rows,
+    branch groups of 8 (M <= 768) and 6 (M = 1024) with a ragged last group, rows cut by chunk boundaries."""
+    dev = torch.device("cuda:0")
+    N, D, C_out = 600, 4, 10
+    g = H.make_graph(N, E, conv, "v1", seed=17, power_law=1.5 if E > 10000 else 0.0)
+    batch_A = H.make_batch(g, B, "v1", seed=17)
+    torch.manual_seed(19)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, C_out, M, D, N, conv), version="v1")
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, C_out, M, D, N, conv, "v1", warm_up_flag=True).load_state_dict(sd)
+    layer = layer.to(dev)
+    layer.use_tail_kernel = 'force'
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    l0 = V._lib.launch_count()
+    c_outs = _run_cuda(layer, batch_A, x, 3, dev, wu=0.8)
+    assert layer.bank.codes_g is not None and V._lib.launch_count() > l0
+    _compare(c_outs, _run_oracle(o, batch_A, x, 3, wu=0.8), layer, o)
+    # the group-major mirror tracks the code table
+    G = layer.bank.G
+    cg = layer.bank.grouped_codes()
+    for k in range(layer.bank.nb):
+        assert torch.equal(cg[k // G, :, k % G], layer.bank.codes[:, k])

@@ -1,0 +1,327 @@
+// Out-of-batch ("tail") message passing with the codebooks of a branch GROUP resident in shared memory.
+//
+// The generic kernel (mp.cu) fetches one 32 B codeword sector per (entry, branch) through L1tex/L2 and is bound
+// by the L1tex wavefront rate (profiles/r1_mp_fwd_ncu_full.txt: 484 M sectors, 1.2 sectors/clk/SM).  For the v1
+// formulation (vq_gnn_v1/utils/dataloader.py:144-192 `mapper` + vq_gnn_v1/models.py:170-223), where every batch
+// row has hundreds of out-of-batch neighbours, this kernel instead
+//   * keeps the de-whitened codebooks O_k of G consecutive branches in shared memory (G*M*32 B <= 192 KB),
+//   * reads the G codes of a neighbour with ONE 16 B load from a group-major copy of the code table
+//     (codes_g [ceil(nb/G)][N][8] int16), i.e. one global sector per (entry, group) instead of G,
+//   * gathers codewords with LDS.128 (16 B chunk index XOR-swizzled so random codes spread over all banks),
+//   * maps lane = entry, accumulates lane-private partial sums for the row, and at the end of a row segment
+//     reduce-scatters the 64 partial sums across the warp (62 shuffles) into vector REDs on y / gq.
+// Work items = (branch group, block of 512-entry chunks), dealt round-robin to one persistent CTA per SM.
+//   y[r, k*4..]  += sum_e val[e] * feat_scale * O_k[code_k(node[e]), :4]
+//   gq[r, k*4..] += sum_e rval[e]            * O_k[code_k(node[e]), 4:8]     ; info += <x[r], gq partial>
+#include "mp_common.cuh"
+
+namespace vqgnn {
+
+constexpr int kTailWarps = 16;
+constexpr int kTailThreads = kTailWarps * 32;
+
+__device__ __forceinline__ void red_v2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// v[0..63] summed over the 32 lanes; lane L ends up with the totals of v[2L] and v[2L+1]
+__device__ __forceinline__ void warp_reduce_scatter64(float (&v)[64], int lane, float& out0, float& out1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const bool up = lane & 16;
+    const float keep = up ? v[i + 32] : v[i], send = up ? v[i] : v[i + 32];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 8;
+    const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 4;
+    const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 2;
+    const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 1;
+    const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  out0 = v[0], out1 = v[1];
+}
+
+template <int G>
+__global__ void __launch_bounds__(kTailThreads, 1)
+    mp_tail_smem_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ node,
+                        const float* __restrict__ val, const float* __restrict__ rval,
+                        const int32_t* __restrict__ chunk_row, int n_chunks, int chunk, int nnz, int B,
+                        const int16_t* __restrict__ codes_g, int64_t N, const float* __restrict__ O, int nb, int M,
+                        const float* __restrict__ x, int64_t ldx, float feat_scale, float* __restrict__ y,
+                        int64_t ldy, float* __restrict__ gq, int64_t ldgq, float* __restrict__ info,
+                        float info_scale, double* ws_sum, unsigned int* ws_count, int ng, int cpi,
+                        int items_per_group) {
+  extern __shared__ __align__(128) unsigned char cb_smem[];  // [G][M] codewords of 32 B, 16 B chunks swizzled
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* cb_ptr = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cb_smem) + 127) & ~uintptr_t(127));
+  const uint32_t cb_base = static_cast<uint32_t>(__cvta_generic_to_shared(cb_ptr));
+  const int branch_bytes = M * 32;
+  __shared__ int next_chunk;  // warps of the CTA draw the item's chunks dynamically
+  float fpart = 0.f;
+  int loaded = -1;
+  const int n_items = ng * items_per_group;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int gk = item / items_per_group;
+    const int cblk = item - gk * items_per_group;
+    const int kbase = gk * G;
+    const int gcount = min(G, nb - kbase);
+    if (gk != loaded) {  // (re)load the group's codebooks: coalesced 16 B loads, swizzled 16 B stores
+      __syncthreads();
+      const int chunks16 = gcount * M * 2;
+      const float4* src = reinterpret_cast<const float4*>(O + static_cast<int64_t>(kbase) * M * 8);
+      for (int c = threadIdx.x; c < chunks16; c += kTailThreads) {
+        const int m = (c >> 1) % M;  // codeword index inside its branch
+        const int sw = (m >> 2) & 1;
+        *reinterpret_cast<float4*>(cb_ptr + static_cast<size_t>(c ^ sw) * 16) = __ldg(src + c);
+      }
+      loaded = gk;
+      __syncthreads();
+    }
+    const int16_t* cg = codes_g + static_cast<int64_t>(gk) * N * 8;
+    const int c_begin = cblk * cpi, c_end = min(c_begin + cpi, n_chunks);
+    __syncthreads();  // every warp is done with the previous item (and its chunk counter)
+    if (threadIdx.x == 0) next_chunk = c_begin;
+    __syncthreads();
+
+    while (true) {
+      int ch = 0;
+      if (lane == 0) ch = atomicAdd(&next_chunk, 1);
+      ch = __shfl_sync(0xffffffffu, ch, 0);
+      if (ch >= c_end) break;
+      const int eb = ch * chunk, ee = min(eb + chunk, nnz);
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      // rows: lane i holds rowptr[rbase + i]
+      int r = __ldg(chunk_row + ch);
+      int rbase = r;
+      int rp_l = __ldg(rowptr + min(rbase + lane, B));
+      int re = __shfl_sync(0xffffffffu, rp_l, 1);
+      bool pending = false;
+
+      // software pipeline: (node, val, rval) two batches ahead, codes one batch ahead
+      int node_n = 0;
+      float v_n = 0.f, rv_n = 0.f;  // batch i+1
+      uint4 cv_n = make_uint4(0, 0, 0, 0);
+      {
+        const int e = eb + lane;
+        if (e < ee) node_n = __ldg(node + e), v_n = __ldg(val + e), rv_n = __ldg(rval + e);
+        cv_n = __ldg(reinterpret_cast<const uint4*>(cg + static_cast<int64_t>(node_n) * 8));
+      }
+      int node_nn = 0;
+      float v_nn = 0.f, rv_nn = 0.f;  // batch i+2
+      {
+        const int e = eb + 32 + lane;
+        if (e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
+      }
+
+      for (int bb = eb; bb < ee; bb += 32) {
+        const float v_l = v_n * feat_scale, rv_l = rv_n;
+        const uint4 cv = cv_n;
+        // advance the pipeline
+        node_n = node_nn, v_n = v_nn, rv_n = rv_nn;
+        cv_n = __ldg(reinterpret_cast<const uint4*>(cg + static_cast<int64_t>(node_n) * 8));
+        {
+          const int e = bb + 64 + lane;
+          node_nn = 0, v_nn = 0.f, rv_nn = 0.f;
+          if (e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
+        }
+        // codeword addresses of this lane's entry
+        uint32_t addr[G];   // feature chunk; the gradient chunk is the other 16 B of the same 32 B codeword
+        const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int gI = 0; gI < G; ++gI) {
+          const uint32_t code = (gI & 1) ? (cw[gI >> 1] >> 16) : (cw[gI >> 1] & 0xffffu);
+          addr[gI] = cb_base + gI * branch_bytes + code * 32 + ((code >> 2) & 1) * 16;  // cb_base is 32 B aligned
+        }
+        const int e = bb + lane;
+        const int bend = min(bb + 32, ee);
+        int j0 = bb;
+        while (j0 < bend) {  // pieces of this batch that belong to one row
+          const int pend = min(re, bend);
+          const bool on = e >= j0 && e < pend;
+          const float vf = on ? v_l : 0.f, vr = on ? rv_l : 0.f;
+#pragma unroll
+          for (int gI = 0; gI < G; ++gI) {
+            if (gI < gcount) {
+              float4 f, q;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                           : "r"(addr[gI]));
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                           : "r"(addr[gI] ^ 16u));  // valid because cb_base is a multiple of 32
+              float* a = acc + gI * 8;
+              a[0] = fmaf(vf, f.x, a[0]), a[1] = fmaf(vf, f.y, a[1]), a[2] = fmaf(vf, f.z, a[2]), a[3] = fmaf(vf, f.w, a[3]);
+              a[4] = fmaf(vr, q.x, a[4]), a[5] = fmaf(vr, q.y, a[5]), a[6] = fmaf(vr, q.z, a[6]), a[7] = fmaf(vr, q.w, a[7]);
+            }
+          }
+          pending = true;
+          j0 = pend;
+          if (pend == re) {  // row r complete: reduce over lanes and accumulate into the outputs
+            float o0, o1;
+            warp_reduce_scatter64(acc, lane, o0, o1);
+            const int gI = lane >> 2, jj = (lane & 3) * 2;
+            if (gI < gcount) {
+              const int colbase = (kbase + gI) * 4 + (jj & 3);
+              if (jj < 4) {
+                red_v2(y + static_cast<int64_t>(r) * ldy + colbase, o0, o1);
+              } else {
+                if (gq) red_v2(gq + static_cast<int64_t>(r) * ldgq + colbase, o0, o1);
+                if (info) {
+                  const float2 xr = __ldg(reinterpret_cast<const float2*>(x + static_cast<int64_t>(r) * ldx + colbase));
+                  fpart = fmaf(xr.x, o0, fmaf(xr.y, o1, fpart));
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+            pending = false;
+            if (j0 >= ee) break;
+            do {
+              ++r;
+              if (r - rbase >= 31) {
+                rbase = r;
+                rp_l = __ldg(rowptr + min(rbase + lane, B));
+              }
+              re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
+            } while (re <= j0);
+          }
+        }
+      }
+      if (pending) {
+        float o0, o1;
+        warp_reduce_scatter64(acc, lane, o0, o1);
+        const int gI = lane >> 2, jj = (lane & 3) * 2;
+        if (gI < gcount) {
+          const int colbase = (kbase + gI) * 4 + (jj & 3);
+          if (jj < 4) {
+            red_v2(y + static_cast<int64_t>(r) * ldy + colbase, o0, o1);
+          } else {
+            if (gq) red_v2(gq + static_cast<int64_t>(r) * ldgq + colbase, o0, o1);
+            if (info) {
+              const float2 xr = __ldg(reinterpret_cast<const float2*>(x + static_cast<int64_t>(r) * ldx + colbase));
+              fpart = fmaf(xr.x, o0, fmaf(xr.y, o1, fpart));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  if (info) {  // CTA reduction of the info partials, "last CTA finishes"
+    __shared__ double sh[kTailWarps];
+    double part = warp_sum(static_cast<double>(fpart));
+    __syncthreads();
+    if (lane == 0) sh[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+#pragma unroll
+      for (int i = 0; i < kTailWarps; ++i) t += sh[i];
+      atomicAdd(ws_sum, t);
+      __threadfence();
+      const unsigned int ticket = atomicAdd(ws_count, 1u);
+      if (ticket == gridDim.x - 1) {
+        const double total = atomicAdd(ws_sum, 0.0);
+        atomicAdd(info, static_cast<float>(static_cast<double>(info_scale) * total));
+      }
+    }
+  }
+}
+
+// codes_g[(k / G) * N + node][k % G] = codes[node, k] for the listed nodes (all N when rows == nullptr)
+__global__ void codes_group_kernel(const int16_t* __restrict__ codes, int nb, const int32_t* __restrict__ rows,
+                                   int64_t n_rows, int64_t N, int G, int16_t* __restrict__ codes_g) {
+  const int64_t total = n_rows * nb;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t rI = i / nb;
+    const int k = static_cast<int>(i - rI * nb);
+    const int64_t nd = rows ? __ldg(rows + rI) : rI;
+    codes_g[((static_cast<int64_t>(k / G)) * N + nd) * 8 + (k % G)] = __ldg(codes + nd * nb + k);
+  }
+}
+
+}  // namespace vqgnn
+
+using namespace vqgnn;
+
+extern "C" int vqgnn_mp_tail_group(int M, int D, int Wp) {
+  if (D != 4 || Wp != 8 || M <= 0) return 0;
+  if (M * 32 * 8 <= 196608) return 8;
+  if (M * 32 * 6 <= 196608) return 6;
+  return 0;
+}
+
+extern "C" int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* rows, int64_t n_rows, int64_t N,
+                                 int G, int16_t* codes_g, void* stream) {
+  VQ_CHECK_ARG(codes && codes_g && nb > 0 && n_rows >= 0 && N > 0 && (G == 6 || G == 8), "codes_group: bad arguments");
+  if (n_rows == 0) return VQGNN_OK;
+  const int grid = static_cast<int>(std::min<int64_t>((n_rows * nb + 255) / 256, 16 * kNumSMs));
+  codes_group_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, nb, rows, n_rows, N, G, codes_g);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}
+
+extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* val, const float* rval,
+                                 const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* x,
+                                 int64_t ldx, const int16_t* codes_g, int64_t N, const float* O, int nb, int M,
+                                 int D, int Wp, float feat_scale, float info_scale, float* y, int64_t ldy,
+                                 float* gq, int64_t ldgq, float* info, void* ws, void* stream) {
+  VQ_CHECK_ARG(rowptr && node && val && rval && x && codes_g && O && y, "mp_fwd_tail: null argument");
+  const int G = vqgnn_mp_tail_group(M, D, Wp);
+  VQ_CHECK_ARG(G != 0, "mp_fwd_tail: needs D == 4, Wp == 8 and M <= 1024 (got M=%d D=%d Wp=%d)", M, D, Wp);
+  VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31) && nb > 0, "mp_fwd_tail: bad sizes");
+  VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_fwd_tail: needs chunk_row");
+  VQ_CHECK_ARG(ldy % 2 == 0 && ldx % 2 == 0 && (!gq || ldgq % 2 == 0) && aligned16(O) && aligned16(codes_g) &&
+                   (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+                   (!gq || (reinterpret_cast<uintptr_t>(gq) & 7) == 0),
+               "mp_fwd_tail: operands must be 8 B aligned with even leading dimensions");
+  VQ_CHECK_ARG(!info || ws, "mp_fwd_tail: info needs a workspace");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n_chunks = static_cast<int>((nnz + chunk - 1) / chunk);
+  if (n_chunks == 0) return VQGNN_OK;
+  const int ng = (nb + G - 1) / G;
+  // items = (group, block of cpi chunks): ~8 items per CTA, dealt round-robin
+  const int grid = kNumSMs;
+  int items_per_group = std::max(1, (grid * 8 + ng - 1) / ng);
+  int cpi = std::max(kTailWarps, (n_chunks + items_per_group - 1) / items_per_group);
+  items_per_group = (n_chunks + cpi - 1) / cpi;
+  double* ws_sum = static_cast<double*>(ws);
+  unsigned int* ws_count = ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 8) : nullptr;
+  if (info) VQ_CUDA(cudaMemsetAsync(ws, 0, 16, s));
+  const size_t smem = static_cast<size_t>(G) * M * 32 + 128;
+#define VQ_TAIL(GG)                                                                                           \
+  do {                                                                                                        \
+    auto kern = mp_tail_smem_kernel<GG>;                                                                      \
+    VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+    kern<<<std::min(grid, ng * items_per_group), kTailThreads, smem, s>>>(                                    \
+        rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, (int)B, codes_g, N, O, nb, M, x, ldx,  \
+        feat_scale, y, ldy, gq, ldgq, info, info_scale, ws_sum, ws_count, ng, cpi, items_per_group);          \
+  } while (0)
+  if (G == 8) VQ_TAIL(8);
+  else VQ_TAIL(6);
+#undef VQ_TAIL
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}

@@ -135,8 +135,46 @@ class BatchPlan:
             self.extras[key] = t
         return t
 
+    def split_v1(self):
+        """v1 plans: the forward CSR split into its in-batch part (dense rows, generic kernel) and its tail
+        part (out-of-batch neighbours, shared-memory codebook kernel).  Built lazily, once per plan.
+        -> dict(inb=(rowptr, col, val, chunk_row, nnz), tail=(rowptr, node, val, rval, chunk_row, nnz))"""
+        sp = self.extras.get('split')
+        if sp is None:
+            from . import _lib
+            assert self.version == 'v1' and self.fwd_rval is not None
+            lib = _lib.load()
+            dev = self.fwd_col.device
+            B = self.B
+            deg = (self.fwd_rowptr[1:] - self.fwd_rowptr[:-1]).long()
+            rows = torch.repeat_interleave(torch.arange(B, device=dev), deg)
+            is_tail = self.fwd_col >= B
+
+            def csr(mask, chunk):
+                r = rows[mask]
+                ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+                ptr[1:] = torch.cumsum(torch.bincount(r, minlength=B), 0).to(torch.int32)
+                nnz = int(r.numel())
+                n = int(lib.vqgnn_mp_num_chunks(nnz, chunk))
+                cr = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+                _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(ptr), B, nnz, chunk, _lib.ptr(cr), _lib.stream()))
+                return ptr, cr, nnz
+
+            tptr, tcr, tnnz = csr(is_tail, TAIL_CHUNK)
+            iptr, icr, innz = csr(~is_tail, MP_CHUNK)
+            sp = dict(
+                tail=(tptr, (self.fwd_col[is_tail] - B).contiguous(), self.fwd_val[is_tail].contiguous(),
+                      self.fwd_rval[is_tail].contiguous(), tcr, tnnz),
+                inb=(iptr, self.fwd_col[~is_tail].contiguous(), self.fwd_val[~is_tail].contiguous(), icr, innz))
+            self.extras['split'] = sp
+        return sp
+
 
 MP_CHUNK = 256   # CSR entries per warp task (multiple of 32)
+
+
+TAIL_CHUNK = 512  # entries per warp task of the shared-memory tail kernel (csrc/mp_tail.cu)
+TAIL_MIN_AVG_DEGREE = 32   # below this the per-row reduce of the lane=entry kernel does not pay
 
 
 def _i32(t: Tensor) -> Tensor:

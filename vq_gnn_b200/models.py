@@ -25,7 +25,7 @@ from torch import nn
 
 from . import _lib
 from .convs import OurGATConv, OurGCNConv, Transformer  # noqa: F401
-from .graph import MP_CHUNK, BatchPlan, CSRAdj, build_plan
+from .graph import MP_CHUNK, TAIL_CHUNK, TAIL_MIN_AVG_DEGREE, BatchPlan, CSRAdj, build_plan
 from .vq import VectorQuantizerEMA, VQBank
 
 Tensor = torch.Tensor
@@ -73,12 +73,34 @@ class VQConvFunction(torch.autograd.Function):
         v1 = plan.version == 'v1'
         gq = torch.empty(B, C, device=dev) if (v1 and plan.fwd_rval is not None) else None
         ws = _mp_ws(dev) if need_info else None
-        _lib.check(lib.vqgnn_mp_fwd(
-            _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
-            _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
-            _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, float(wu) if v1 else 1.0, float(wu),
-            _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
-            _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+        codes_g = None
+        if v1 and gq is not None and layer.use_tail_kernel and (
+                layer.use_tail_kernel == 'force' or plan.nnz >= TAIL_MIN_AVG_DEGREE * B):
+            codes_g = bank.grouped_codes()
+        if codes_g is not None:
+            # in-batch entries through the generic kernel (zero-initialises y), then the out-of-batch entries
+            # through the shared-memory codebook kernel, which accumulates on top (csrc/mp_tail.cu)
+            sp = plan.split_v1()
+            iptr, icol, ival, icr, innz = sp['inb']
+            tptr, tnode, tval, trval, tcr, tnnz = sp['tail']
+            _lib.check(lib.vqgnn_mp_fwd(
+                _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), None, _lib.ptr(icr), MP_CHUNK, innz, B, B,
+                _lib.ptr(x), x.stride(0), None, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
+                bank.Wp, 1.0, 1.0, _lib.ptr(y), y.stride(0), None, 0, None, None, st))
+            gq.zero_()
+            _lib.check(lib.vqgnn_mp_fwd_tail(
+                _lib.ptr(tptr), _lib.ptr(tnode), _lib.ptr(tval), _lib.ptr(trval), _lib.ptr(tcr), TAIL_CHUNK, tnnz,
+                B, _lib.ptr(x), x.stride(0), _lib.ptr(codes_g), codes_g.shape[1], _lib.ptr(bank.O), bank.nb,
+                bank.M, bank.D, bank.Wp, float(wu), float(wu), _lib.ptr(y), y.stride(0), _lib.ptr(gq),
+                gq.stride(0), _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+        else:
+            _lib.check(lib.vqgnn_mp_fwd(
+                _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
+                _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
+                _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
+                _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, float(wu) if v1 else 1.0, float(wu),
+                _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
+                _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
         ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook = layer, plan, float(wu), fire_hook
         ctx.save_for_backward(x, gq)
         return y, info
@@ -241,6 +263,9 @@ class LowRankGNNLayer(nn.Module):
                       warm_up_flag=warm_up_flag, momentum=momentum, add_flag=add_flag, num_N=num_N)
         object.__setattr__(self, 'bank', bank)
         self.sync_status = False
+        # shared-memory codebook kernel for the v1 out-of-batch entries: True = when the average row is long
+        # enough (graph.TAIL_MIN_AVG_DEGREE), 'force' = whenever the shape allows, False = never
+        self.use_tail_kernel = True
         self._restack()
 
     # ---- stacked storage <-> per-branch reference buffers -------------------------------------
@@ -259,6 +284,7 @@ class LowRankGNNLayer(nn.Module):
             b.vq._owns_bank = False
             b.vq._bind_views(bank, i)
             b._buffers['c_indices'] = bank.codes[:, i]
+        bank.mark_codes_dirty()
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
@@ -266,6 +292,7 @@ class LowRankGNNLayer(nn.Module):
         return out
 
     def _load_from_state_dict(self, *a, **k):
+        self.bank.mark_codes_dirty()
         return super()._load_from_state_dict(*a, **k)   # buffers are views: copy_ writes through
 
     # ---- reference bookkeeping ----------------------------------------------------------------

@@ -61,6 +61,10 @@ class VQBank:
         self.codes = z(max(num_N, 1), nb, dt=torch.int16)   # [N, nb]
         self.status = z(1, dt=torch.int32)
         self.last_idx: Optional[Tensor] = None
+        # group-major mirror of the code table for the shared-memory tail kernel (csrc/mp_tail.cu)
+        self.G = 0                   # branches per group; resolved on the device (vqgnn_mp_tail_group)
+        self.codes_g: Optional[Tensor] = None
+        self._codes_g_dirty = True
 
     TENSORS = ("E", "O", "Wm", "size", "rm_f", "rv_f", "rm_g", "rv_g", "nbt_f", "nbt_g", "codes", "status")
 
@@ -71,7 +75,31 @@ class VQBank:
     def to(self, device):
         for n in self.TENSORS:
             setattr(self, n, getattr(self, n).to(device))
+        self.codes_g, self._codes_g_dirty = None, True
         return self
+
+    def mark_codes_dirty(self):
+        """Call after writing `codes` (or a per-branch `c_indices` view) from outside the library."""
+        self._codes_g_dirty = True
+
+    def grouped_codes(self) -> Optional[Tensor]:
+        """codes_g [ceil(nb/G), N, 8] int16 (None when the shape has no shared-memory path)."""
+        lib = _lib.load()
+        if self.G == 0:
+            self.G = int(lib.vqgnn_mp_tail_group(self.M, self.D, self.Wp))
+            if self.G == 0:
+                self.G = -1
+        if self.G < 0:
+            return None
+        if self.codes_g is None or self._codes_g_dirty:
+            N = self.codes.shape[0]
+            ng = (self.nb + self.G - 1) // self.G
+            if self.codes_g is None:
+                self.codes_g = torch.zeros(ng, N, 8, dtype=torch.int16, device=self.codes.device)
+            _lib.check(lib.vqgnn_codes_group(_lib.ptr(self.codes), self.nb, None, N, N, self.G,
+                                             _lib.ptr(self.codes_g), _lib.stream()))
+            self._codes_g_dirty = False
+        return self.codes_g
 
     # ---- the fused update ---------------------------------------------------------------------
     def run(self, x: Tensor, g: Optional[Tensor], batch_idx: Optional[Tensor], training: bool,
@@ -148,6 +176,12 @@ class VQBank:
                 1 if self.warm_up_flag else 0, self.eps, self.scale[0], self.scale[1], _lib.ptr(rm_f),
                 _lib.ptr(rv_f), _lib.ptr(rm_g) if joint else None, _lib.ptr(rv_g) if joint else None,
                 _lib.ptr(size), _lib.ptr(Wm), _lib.ptr(E), _lib.ptr(O), _lib.ptr(self.status), st))
+        if codes_ptr is not None and self.codes_g is not None and not self._codes_g_dirty:
+            if k0 == 0 and nbc == self.nb:    # keep the group-major mirror in step (batch rows only)
+                _lib.check(lib.vqgnn_codes_group(_lib.ptr(self.codes), self.nb, _lib.ptr(bidx), B,
+                                                 self.codes.shape[0], self.G, _lib.ptr(self.codes_g), st))
+            else:
+                self._codes_g_dirty = True
         self.last_idx = idx
         self.last_stats = stats
         return idx
