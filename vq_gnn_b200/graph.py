@@ -135,6 +135,17 @@ class BatchPlan:
             self.extras[key] = t
         return t
 
+    def warm(self, split: bool = True) -> "BatchPlan":
+        """Build every lazily-derived piece now (on the current stream): the work partitions and, for v1
+        plans with long rows, the in-batch / tail split.  `LowRankGNN.prepare` calls this so that a prefetching
+        loader pays for it (and its host syncs) off the training stream."""
+        self.chunk_rows('fwd')
+        self.chunk_rows('bwd')
+        if (split and self.version == 'v1' and self.fwd_rval is not None
+                and self.nnz >= TAIL_MIN_AVG_DEGREE * self.B):
+            self.split_v1()
+        return self
+
     def split_v1(self):
         """v1 plans: the forward CSR split into its in-batch part (dense rows, generic kernel) and its tail
         part (out-of-batch neighbours, shared-memory codebook kernel).  Built lazily, once per plan.

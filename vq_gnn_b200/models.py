@@ -388,7 +388,8 @@ class LowRankGNN(nn.Module):
     def prepare(self, batch_A, device=None) -> BatchPlan:
         """Build the kernel plan once per mini-batch (shared by all layers)."""
         device = device or next(self.parameters()).device
-        return build_plan(batch_A, self.conv_type, self.num_N, self.training, device)
+        plan = build_plan(batch_A, self.conv_type, self.num_N, self.training, device)
+        return plan.warm() if plan.fwd_col.is_cuda else plan
 
     def forward(self, batch, warm_up_rate=1, unlabeled=False):
         losses_full, info_backwards_full = 0, 0
