@@ -216,6 +216,38 @@ int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const float* val, c
                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Message passing, GAT, v1 ("B+M") formulation: vq_gnn_v1/models.py:143-233 + `mapper`
+ * (vq_gnn_v1/utils/dataloader.py:144-192) + OurGATConv (vq_gnn_v1/convs.py).  Every branch is an independent
+ * GAT over B batch rows and M codewords with D+1 = 5 columns and its own att_l / att_r ([nb, 5] stacked);
+ * needs num_D = 4 and the add_flag codebook layout (Wp = 12: 4 feature | 4+1 gradient | pad).
+ * CSR = the v1 plan (col < B in-batch incl. the self loop, col >= B tail entry with node id col - B; rval =
+ * A_NB_v reverse values, may be NULL in eval).
+ * ------------------------------------------------------------------------------------------- */
+
+/* a_l / a_r [B, nb] (batch rows), cs [nb, M, 2] (codewords: c_l, c_r; features wu * O_k[m, :4]),
+ * stat [nb, 2] = per-branch maxima of the l / r scores over batch rows and codewords (convs.py:209). */
+int vqgnn_gat1_scores(int64_t B, const float* x, int64_t ldx, const float* O, int nb, int M, int D, int Wp,
+                      float wu, const float* att_l, const float* att_r, float* a_l, float* a_r, float* cs,
+                      float* stat, void* stream);
+/* y [B, nb*4] = per-branch normalised outputs (models.py:209-210), den [B, nb] the ones-column sums,
+ * *info = wu * sum over branches of <X_out_M, gradient codewords> (models.py:223) when info != NULL. */
+int vqgnn_gat1_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
+                   const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* x, int64_t ldx,
+                   const int16_t* codes, const float* O, int nb, int M, int D, int Wp, float wu, const float* a_l,
+                   const float* a_r, const float* cs, const float* stat, float negative_slope, float* y,
+                   int64_t ldy, float* den, float* info, void* ws, void* stream);
+/* Backward.  gy [B, nb*5] = d loss / d (un-normalised X_out_B) per branch, i.e. the VQ hook's gradient
+ * (models.py:199-203, add_flag width D+1); dx [B, nb*4] (may be NULL); datt_l / datt_r [nb, 5];
+ * scratch ds [B, nb, 2], dcs [nb, M, 2]. */
+int vqgnn_gat1_bwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
+                   const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* x, int64_t ldx,
+                   const int16_t* codes, const float* O, int nb, int M, int D, int Wp, float wu,
+                   const float* att_l, const float* att_r, const float* a_l, const float* a_r, const float* cs,
+                   const float* stat, float negative_slope, const float* out, int64_t ldo, const float* den,
+                   const float* dout, int64_t lddo, const float* dinfo, float* gy, float* ds, float* dcs,
+                   float* dx, int64_t lddx, float* datt_l, float* datt_r, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * helpers
  * ------------------------------------------------------------------------------------------- */
 int vqgnn_fill_zero(void* ptr, size_t bytes, void* stream);

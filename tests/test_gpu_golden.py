@@ -35,8 +35,6 @@ def test_cuda_vq_matches_golden(name):
 
 @pytest.mark.parametrize("name", LAYER_FILES)
 def test_cuda_layer_matches_golden(name):
-    if name == "layer_v1_gat":
-        pytest.skip("v1 per-branch GAT (B+M graphs, D+1 columns) is the next row of DESIGN.md's scope table")
     dev = torch.device("cuda:0")
     z = H.load_golden(name)
     version, conv = str(z["meta.version"]), str(z["meta.conv"])

@@ -65,7 +65,8 @@ CASES = [("v2", "GCN", 8, 4, False), ("v2", "SAGE", 8, 4, False), ("v1", "GCN", 
          ("v1", "SAGE", 8, 4, False), ("v2", "GCN", 128, 4, True), ("v1", "SAGE", 128, 4, False),
          ("v2", "SAGE", 12, 2, False), ("v1", "GCN", 24, 8, True), ("v2", "GCN", 52, 4, False),
          ("v2", "GAT", 8, 4, True), ("v2", "GAT", 128, 4, True), ("v2", "GAT", 52, 4, False),
-         ("v2", "GAT", 12, 2, True), ("v2", "GAT", 260, 4, True)]
+         ("v2", "GAT", 12, 2, True), ("v2", "GAT", 260, 4, True),
+         ("v1", "GAT", 8, 4, True), ("v1", "GAT", 128, 4, False), ("v1", "GAT", 52, 4, True)]
 
 
 @pytest.mark.parametrize("version,conv,C,D,skip", CASES)
@@ -182,7 +183,7 @@ def test_full_model_train_step_matches_oracle_stack():
 
 
 @pytest.mark.parametrize("version,conv", [("v1", "SAGE"), ("v1", "GCN"), ("v2", "GCN"), ("v2", "SAGE"),
-                                          ("v2", "GAT")])
+                                          ("v2", "GAT"), ("v1", "GAT")])
 def test_hub_rows_cut_by_chunk_boundaries(version, conv):
     """Power-law graph whose hub rows hold thousands of entries (>> the 256-entry warp chunk of the
     message-passing kernels) next to empty rows: exercises the RED-accumulated partial rows."""

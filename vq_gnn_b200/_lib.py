@@ -50,6 +50,12 @@ _SIGNATURES = {
     "vqgnn_gat_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i32, i64, vp, i64, vp, vp, vp,
                                 i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, i64, vp, vp, i64, f32, vp,
                                 vp, i64, vp, vp, vp, vp, i64, vp, vp, vp]),
+    "vqgnn_gat1_scores": (C.c_int, [i64, vp, i64, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "vqgnn_gat1_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i64, vp, i64, vp, vp, i32, i32, i32, i32, f32,
+                                 vp, vp, vp, vp, f32, vp, i64, vp, vp, vp, vp]),
+    "vqgnn_gat1_bwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i64, vp, i64, vp, vp, i32, i32, i32, i32, f32,
+                                 vp, vp, vp, vp, vp, vp, f32, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64,
+                                 vp, vp, vp]),
     "vqgnn_fill_zero": (C.c_int, [vp, C.c_size_t, vp]),
     "vqgnn_flush_l2": (C.c_int, [vp, C.c_size_t, vp]),
     "vqgnn_codes_pack": (C.c_int, [vp, i32, i64, vp, vp]),

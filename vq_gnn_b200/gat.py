@@ -81,8 +81,77 @@ class VQGATFunction(torch.autograd.Function):
         return dx, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), None, None, None, None, None
 
 
+class VQGAT1Function(torch.autograd.Function):
+    """v1 per-branch GAT: `LowRankGNNBlock.forward` for all branches at once (vq_gnn_v1/models.py:143-233 with
+    `mapper`, vq_gnn_v1/utils/dataloader.py:144-192).  att_l / att_r: [nb, 5] (the blocks' parameters stacked)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, att_l: Tensor, att_r: Tensor, layer, plan: BatchPlan, wu: float,
+                fire_hook: bool, slope: float):
+        _lib.require_device(x)
+        lib, st = _lib.load(), _lib.stream()
+        bank = layer.bank
+        B, C = x.shape
+        nb, M, dev = bank.nb, bank.M, x.device
+        al, ar = att_l.detach().contiguous(), att_r.detach().contiguous()
+        a_l, a_r = torch.empty(B, nb, device=dev), torch.empty(B, nb, device=dev)
+        cs, stat = torch.empty(nb, M, 2, device=dev), torch.empty(nb, 2, device=dev)
+        _lib.check(lib.vqgnn_gat1_scores(B, _lib.ptr(x), x.stride(0), _lib.ptr(bank.O), nb, M, bank.D, bank.Wp,
+                                         float(wu), _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r),
+                                         _lib.ptr(cs), _lib.ptr(stat), st))
+        y, den = torch.empty(B, C, device=dev), torch.empty(B, nb, device=dev)
+        need_info = plan.training and plan.fwd_rval is not None
+        info = torch.zeros((), device=dev)
+        ws = torch.empty(8, dtype=torch.float64, device=dev) if need_info else None
+        _lib.check(lib.vqgnn_gat1_fwd(
+            _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
+            _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, B, _lib.ptr(x), x.stride(0), _lib.ptr(bank.codes),
+            _lib.ptr(bank.O), nb, M, bank.D, bank.Wp, float(wu), _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(cs),
+            _lib.ptr(stat), float(slope), _lib.ptr(y), y.stride(0), _lib.ptr(den),
+            _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+        ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook, ctx.slope = layer, plan, float(wu), fire_hook, float(slope)
+        ctx.save_for_backward(x, al, ar, a_l, a_r, cs, stat, y, den)
+        return y, info
+
+    @staticmethod
+    def backward(ctx, dy: Tensor, dinfo: Tensor):
+        x, al, ar, a_l, a_r, cs, stat, y, den = ctx.saved_tensors
+        layer, plan, wu = ctx.layer, ctx.plan, ctx.wu
+        lib, st = _lib.load(), _lib.stream()
+        bank = layer.bank
+        B, C = x.shape
+        nb, M, dev = bank.nb, bank.M, x.device
+        if plan.fwd_rval is None:
+            raise RuntimeError("the v1 GAT backward needs a training plan (reverse values A_NB_v)")
+        dy = dy.contiguous().float()
+        dinfo = dinfo.contiguous().float()
+        gy = torch.empty(B, nb * 5, device=dev)
+        ds, dcs = torch.empty(B, nb, 2, device=dev), torch.empty(nb, M, 2, device=dev)
+        datt_l, datt_r = torch.empty(nb, 5, device=dev), torch.empty(nb, 5, device=dev)
+        dx = torch.empty(B, C, device=dev) if ctx.needs_input_grad[0] else None
+        _lib.check(lib.vqgnn_gat1_bwd(
+            _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
+            _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, B, _lib.ptr(x), x.stride(0), _lib.ptr(bank.codes),
+            _lib.ptr(bank.O), nb, M, bank.D, bank.Wp, wu, _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r),
+            _lib.ptr(cs), _lib.ptr(stat), ctx.slope, _lib.ptr(y), y.stride(0), _lib.ptr(den), _lib.ptr(dy),
+            dy.stride(0), _lib.ptr(dinfo), _lib.ptr(gy), _lib.ptr(ds), _lib.ptr(dcs), _lib.ptr(dx),
+            dx.stride(0) if dx is not None else 0, _lib.ptr(datt_l), _lib.ptr(datt_r), st))
+        if ctx.fire_hook:
+            # hook(grad) on X_output_B [B, D+1] of every branch (vq_gnn_v1/models.py:199-203): add_flag width
+            bank.run(x, gy, plan.batch_idx, True)
+        return dx, datt_l, datt_r, None, None, None, None, None
+
+
 def gat_conv(layer, x: Tensor, plan: BatchPlan, wu: float, fire_hook: bool):
     """-> (y [B, C] normalised batch rows, info_backward scalar)."""
+    if plan.version == 'v1':
+        convs = [b.conv for b in layer.gnn_block]
+        att_l = torch.stack([c.att_l.reshape(-1) for c in convs])       # [nb, D+1]
+        att_r = torch.stack([c.att_r.reshape(-1) for c in convs])
+        if layer.num_D != 4:
+            raise NotImplementedError("the v1 GAT kernels are written for num_D = 4 (every reference config)")
+        return VQGAT1Function.apply(x, att_l, att_r, layer, plan, float(wu), fire_hook,
+                                    float(convs[0].negative_slope))
     if plan.version != 'v2':
         raise NotImplementedError("GAT is implemented for the v2 (B+B') formulation; the v1 per-branch "
                                   "(B+M, D+1 columns, add_flag quantiser) GAT is the next row (DESIGN.md)")
