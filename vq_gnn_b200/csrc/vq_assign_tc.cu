@@ -11,12 +11,13 @@
 // what keeps the argmin on the fp32 answer except at near-ties (tests report the mismatch rate).
 //
 // Persistent CTAs (one per SM, all 512 TMEM columns = two 128x256 fp32 accumulators).  Work item =
-// (branch, 128-row tile); per item the 8 epilogue warps whiten their rows and write the A' tile into shared
+// (branch, 128-row tile); per item the 16 epilogue warps whiten their rows and write the A' tile into shared
 // memory in the canonical K-major UMMA layout, then for every 256-codeword tile of the branch:
-//   warp 8 (one lane)  TMA producer : cp.async.bulk of the pre-packed 32 KB B' tile into a 3-stage ring
-//   warp 9 (one lane)  MMA issuer   : 4 x tcgen05.mma (128x256x8, tf32) into accumulator buffer (tile & 1),
+//   warp 16 (one lane) TMA producer : cp.async.bulk of the pre-packed 32 KB B' tile into a 3-stage ring
+//   warp 17 (one lane) MMA issuer   : 4 x tcgen05.mma (128x256x8, tf32) into accumulator buffer (tile & 1),
 //                                     tcgen05.commit -> frees the smem stage and publishes the accumulator
-//   warps 0-7          epilogue     : tcgen05.ld 32 columns at a time, running (min, argmin) per row
+//   warps 0-15         epilogue     : 4 warps per TMEM lane quarter, 64 columns each: two tcgen05.ld in flight,
+//                                     buffer released as soon as they land, running (min, argmin) per row
 // and finally the code is written (idx, code table scatter) and z is added to the per-codeword sums/counts.
 #include "common.cuh"
 
@@ -26,8 +27,9 @@ namespace tc {
 constexpr int kTileM = 128;           // rows per work item (= TMEM lanes)
 constexpr int kTileN = 256;           // codewords per MMA tile (= TMEM columns per accumulator)
 constexpr int kK = 32;                // packed contraction length (tf32 elements)
-constexpr int kStages = 3;            // B' smem ring
-constexpr int kEpiThreads = 256;      // warps 0..7
+constexpr int kStages = 4;            // B' smem stages: a ring when streaming, the whole branch when M <= 1024
+constexpr int kEpiWarps = 16;         // 4 warps per TMEM lane quarter, 64 accumulator columns each
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = kEpiThreads + 64;
 constexpr int kATileBytes = kTileM * kK * 4;   // 16 KB
 constexpr int kBTileBytes = kTileN * kK * 4;   // 32 KB
@@ -100,8 +102,7 @@ __device__ __forceinline__ float to_tf32(float v) {
   return __uint_as_float(r);
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -111,10 +112,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // B' packer: [nb][M_pad/256][K chunk 8][row group 32][row 8][4] fp32 (TF32-exact values), i.e. every
@@ -168,8 +167,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned char* misc = b_tiles + kStages * kBTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // [0..2] b_full, [3..5] b_empty, [6..7] acc_full, [8..9] acc_empty, [10] a_ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
-  float* xbest = reinterpret_cast<float*>(misc + 256);      // [128] candidates of the upper column half
-  int* xidx = reinterpret_cast<int*>(misc + 256 + 512);      // [128]
+  float* xbest = reinterpret_cast<float*>(misc + 256);           // [3][128] candidates of column quarters 1..3
+  int* xidx = reinterpret_cast<int*>(misc + 256 + 3 * 512);      // [3][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -183,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     mbar_init(BAR(A_READY), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
+  if (warp == kEpiWarps + 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -196,35 +195,49 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int row_tiles = static_cast<int>((B + kTileM - 1) / kTileM);
   const int64_t n_items = static_cast<int64_t>(nb) * row_tiles;
   const int C = nb * D;
+  // every CTA owns a CONTIGUOUS range of (branch-major) items, so consecutive items share the branch; when the
+  // branch's whole packed codebook fits the stages (M <= 1024) it stays resident in shared memory and is fetched
+  // once per branch instead of once per item (the per-item refetch made the first version L2-bound)
+  const int64_t ipc = (n_items + gridDim.x - 1) / gridDim.x;
+  const int64_t item_begin = blockIdx.x * ipc, item_end = min(n_items, item_begin + ipc);
+  const bool resident = tiles_per_item <= kStages;
 
-  if (warp == 8) {
+  if (warp == kEpiWarps) {
     // ===== TMA producer =====
     if (lane == 0) {
-      uint32_t gt = 0;
-      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      uint32_t gt = 0, it = 0;
+      int loaded = -1;
+      for (int64_t item = item_begin; item < item_end; ++item, ++it) {
         const int k = static_cast<int>(item / row_tiles);
         const char* src = reinterpret_cast<const char*>(Bp) + static_cast<int64_t>(k) * tiles_per_item * kBTileBytes;
         for (int j = 0; j < tiles_per_item; ++j, ++gt) {
-          const int s = gt % kStages;
-          mbar_wait(BAR(B_EMPTY + s), ((gt / kStages) & 1) ^ 1);
-          mbar_expect_tx(BAR(B_FULL + s), kBTileBytes);
-          tma_bulk_load(smem_u32(b_tiles + s * kBTileBytes), src + static_cast<int64_t>(j) * kBTileBytes, kBTileBytes,
-                        BAR(B_FULL + s));
+          const int s = resident ? j : gt % kStages;
+          const uint32_t use = resident ? it : gt / kStages;
+          mbar_wait(BAR(B_EMPTY + s), (use & 1) ^ 1);
+          if (resident && k == loaded) {
+            mbar_arrive(BAR(B_FULL + s));  // tile already in shared memory: just pass the token
+          } else {
+            mbar_expect_tx(BAR(B_FULL + s), kBTileBytes);
+            tma_bulk_load(smem_u32(b_tiles + s * kBTileBytes), src + static_cast<int64_t>(j) * kBTileBytes, kBTileBytes,
+                          BAR(B_FULL + s));
+          }
         }
+        loaded = k;
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == kEpiWarps + 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t gt = 0, it = 0;
       const uint32_t a_addr = smem_u32(a_tile);
-      for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      for (int64_t item = item_begin; item < item_end; ++item, ++it) {
         mbar_wait(BAR(A_READY), it & 1);
         for (int j = 0; j < tiles_per_item; ++j, ++gt) {
-          const int s = gt % kStages, buf = gt & 1;
+          const int s = resident ? j : gt % kStages, buf = gt & 1;
+          const uint32_t use = resident ? it : gt / kStages;
           mbar_wait(BAR(ACC_EMPTY + buf), ((gt >> 1) & 1) ^ 1);
-          mbar_wait(BAR(B_FULL + s), (gt / kStages) & 1);
+          mbar_wait(BAR(B_FULL + s), use & 1);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_tiles + s * kBTileBytes);
 #pragma unroll
@@ -239,11 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     __syncwarp();
   } else {
-    // ===== A' builders + epilogue (warps 0..7) =====
-    const int q = warp & 3, h = warp >> 2;
+    // ===== A' builders + epilogue (warps 0..15) =====
+    const int q = warp & 3, h = warp >> 2;  // TMEM lane quarter, column quarter (64 of the tile's 256)
     const int rl = 32 * q + lane;  // row inside the tile == TMEM lane
     uint32_t gt = 0;
-    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int64_t item = item_begin; item < item_end; ++item) {
       const int k = static_cast<int>(item / row_tiles);
       const int64_t b = (item - static_cast<int64_t>(k) * row_tiles) * kTileM + rl;
       // ---- whiten the row, split into TF32 hi/lo, write this thread's half of the A' row ----
@@ -271,13 +284,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       {
         unsigned char* dst = a_tile + (rl >> 3) * 128 + (rl & 7) * 16;
 #pragma unroll
-        for (int kk = 0; kk < kK / 4; ++kk) {  // this thread's half of the K chunks (compile-time register indices)
-          if ((kk >> 2) == h)
+        for (int kk = 0; kk < kK / 4; ++kk) {  // this thread's quarter of the K chunks (compile-time register indices)
+          if ((kk >> 1) == h)
             *reinterpret_cast<float4*>(dst + kk * kALbo) = make_float4(a[4 * kk], a[4 * kk + 1], a[4 * kk + 2], a[4 * kk + 3]);
         }
       }
       fence_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (threadIdx.x == 0) mbar_arrive(BAR(A_READY));
 
       // ---- scan the accumulator tiles ----
@@ -287,11 +300,18 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int buf = gt & 1;
         mbar_wait(BAR(ACC_FULL + buf), (gt >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * kTileN + 128 * h;
-#pragma unroll 1
-        for (int cchunk = 0; cchunk < 4; ++cchunk) {
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + buf * kTileN + 64 * h;
+        uint32_t r0[32], r1[32];
+        tmem_ld32_issue(taddr, r0);       // both 32-column chunks in flight before the first use
+        tmem_ld32_issue(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(BAR(ACC_EMPTY + buf));  // the accumulator is in registers: hand the buffer back early
+#pragma unroll
+        for (int cchunk = 0; cchunk < 2; ++cchunk) {
           float v[32];
-          tmem_ld32(taddr + 32 * cchunk, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(cchunk == 0 ? r0[i] : r1[i]);
           float m = v[0];
 #pragma unroll
           for (int i = 1; i < 32; ++i) m = fminf(m, v[i]);
@@ -299,19 +319,20 @@ __global__ void __launch_bounds__(kThreads, 1)
             int at = 31;
 #pragma unroll
             for (int i = 30; i >= 0; --i) at = (v[i] == m) ? i : at;
-            best = m, besti = j * kTileN + 128 * h + 32 * cchunk + at;
+            best = m, besti = j * kTileN + 64 * h + 32 * cchunk + at;
           }
         }
-        tc_fence_before();
-        mbar_arrive(BAR(ACC_EMPTY + buf));
       }
       // ---- combine the two column halves of every row, emit code + statistics ----
-      if (h == 1) xbest[rl] = best, xidx[rl] = besti;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h > 0) xbest[(h - 1) * kTileM + rl] = best, xidx[(h - 1) * kTileM + rl] = besti;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (h == 0 && b < B) {
-        const float ob = xbest[rl];
-        const int oi = xidx[rl];
-        if (ob < best || (ob == best && oi < besti)) besti = oi;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float ob = xbest[o * kTileM + rl];
+          const int oi = xidx[o * kTileM + rl];
+          if (ob < best || (ob == best && oi < besti)) best = ob, besti = oi;
+        }
         const int code = besti;
         if (idx) idx[b * nb + k] = static_cast<int16_t>(code);
         if (codes) codes[static_cast<int64_t>(__ldg(batch_idx + b)) * codes_ld + k] = static_cast<int16_t>(code);
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kEpiWarps + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
