@@ -248,6 +248,8 @@ def main():
     ap.add_argument("--assign-impl", type=int, default=int(os.environ.get("VQGNN_ASSIGN_IMPL", "1")),
                     help="1 = tcgen05/TMEM assignment kernel (default), 0 = exact-fp32 SIMT kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true",
+                    help="launch the device-resident steps eagerly instead of replaying one CUDA graph per batch")
     ap.add_argument("--cpu-branches", type=int, default=4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -262,7 +264,8 @@ def main():
               "step": "3-layer fwd + CE loss + bwd (VQ assign + EMA update of every layer inside bwd) + RMSprop",
               "value_formula": "B * num_layers / t_step", "batch_nodes": c["B"], "num_layers": c["layers"],
               "parallelism": f"dp{world} (node-partitioned batches; EMA stats + weight grads allreduced)",
-              "l2": "4 distinct batches rotated AND a 256 MiB L2 flush between timed steps"}
+              "l2": "4 distinct batches rotated AND a 256 MiB L2 flush between timed steps",
+              "launch": "one CUDA graph per resident batch (whole train step incl. NCCL) replayed; --no-graphs = eager"}
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -302,7 +305,9 @@ def main():
     g, batches = build_workload(dev, rank, world, args.scale)
     N = g.N
     model = build_model(dev, N, distributed, args.assign_impl)
-    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, alpha=0.99)
+    use_graphs = not args.no_graphs
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, alpha=0.99, capturable=use_graphs)
+    opt_eager = torch.optim.RMSprop(model.parameters(), lr=1e-3, alpha=0.99) if use_graphs else opt
     warm_start(model, batches)
     plans = [model.prepare(b[1]) for b in batches]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -321,6 +326,41 @@ def main():
         x, _, y = batches[i % len(batches)]
         train_step(model, opt, x, plans[i % len(plans)], y, distributed)
     sync_all()
+    # The step is launch-bound (~550 kernel launches, ~5 ms of kernels): capture one CUDA graph per resident batch
+    # (the plan's shapes differ per batch) and replay it, so the GPU is never waiting on Python.  Every kernel of
+    # the step -- forward, backward, the VQ updates, the NCCL allreduces and the optimiser -- is inside the graph.
+    graphs, graph_launches = None, []
+    if use_graphs:
+        try:
+            graphs = []
+            side_cap = torch.cuda.Stream(device=dev)
+            for bi, (x, _, y) in enumerate(batches):
+                side_cap.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side_cap):
+                    train_step(model, opt, x, plans[bi], y, distributed)       # allocator warm-up on the side stream
+                torch.cuda.current_stream().wait_stream(side_cap)
+                gph = torch.cuda.CUDAGraph()
+                lc0 = _lib.launch_count()
+                with torch.cuda.graph(gph):
+                    train_step(model, opt, x, plans[bi], y, distributed)
+                graph_launches.append(_lib.launch_count() - lc0)
+                graphs.append(gph)
+            sync_all()
+            for gph in graphs:      # one replay each: first-replay initialisation stays out of the timed region
+                gph.replay()
+            sync_all()
+        except Exception as e:   # capture is an optimisation, never a requirement
+            log(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+            graphs = None
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % len(graphs)].replay()
+        else:
+            x, _, y = batches[i % len(batches)]
+            train_step(model, opt, x, plans[i % len(plans)], y, distributed)
+    sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = _lib.launch_count()
@@ -330,15 +370,16 @@ def main():
     if cuprof:
         torch.cuda.profiler.start()
     for i in range(args.steps):
-        x, _, y = batches[i % len(batches)]
         flush_l2()
         ev[i][0].record()
-        train_step(model, opt, x, plans[i % len(plans)], y, distributed)
+        run_step(i)
         ev[i][1].record()
     sync_all()
     if cuprof:
         torch.cuda.profiler.stop()
     launches = _lib.launch_count() - l0 - args.steps   # minus the flush launches
+    if graphs is not None:   # launches replayed from the graphs (counted once, at capture)
+        launches = sum(graph_launches[i % len(graphs)] for i in range(args.steps))
     clocks = sampler.stop()
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     t_t = torch.tensor([t_ms], dtype=torch.float64, device=dev)
@@ -396,7 +437,7 @@ def main():
         for i in range(n):
             x, plan, y = pf.next()
             flush_l2()
-            loss = train_step(model, opt, x, plan, y, distributed)
+            loss = train_step(model, opt_eager, x, plan, y, distributed)
             last = float(loss.item())                                          # D2H read of the step's result
         pf.drain()
         return last
@@ -424,7 +465,7 @@ def main():
             x, _, y = batches[i % len(batches)]
             flush_l2()
             a0.record()
-            train_step(model, opt, x, plans[i % len(plans)], y, False if not distributed else distributed)
+            train_step(model, opt_eager, x, plans[i % len(plans)], y, distributed)
             a1.record()
             torch.cuda.synchronize()
             tot += a0.elapsed_time(a1)
@@ -481,11 +522,15 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "nodes/s/layer", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "replica_max_abs_diff": replica_div, "kernels": kernel_table, "assign_impl": "tcgen05" if args.assign_impl == 1 else "simt-fp32"}
+                "replica_max_abs_diff": replica_div, "cuda_graphs": graphs is not None, "kernels": kernel_table, "assign_impl": "tcgen05" if args.assign_impl == 1 else "simt-fp32"}
         print(json.dumps(line), flush=True)
     if distributed:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush(), sys.stderr.flush()
+        # captured graphs hold NCCL work: tearing the process group down under them can hang, and the JSON line is
+        # already out -- leave without running destructors
+        os._exit(0)
 
 
 if __name__ == "__main__":

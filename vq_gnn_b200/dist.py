@@ -30,10 +30,23 @@ def partition_range(N: int, rank: int, world_size: int) -> Tuple[int, int]:
     return rank * N // world_size, (rank + 1) * N // world_size
 
 
+def _timed(name: str, fn):
+    """Run fn() bracketed by CUDA events when bench.py's per-kernel attribution is on."""
+    from . import _lib
+    if not (_lib.PROFILER.enabled and torch.cuda.is_available()):
+        return fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    out = fn()
+    b.record()
+    _lib.PROFILER.records.append((name, a, b, None))
+    return out
+
+
 def allreduce_sum_(t: Tensor, group=None) -> Tensor:
     """In-place sum over ranks; a no-op for a single process."""
     if world(group)[1] > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        _timed("nccl_allreduce_stats", lambda: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group))
     return t
 
 
@@ -46,7 +59,7 @@ def allreduce_mean_grads_(params: Iterable[Tensor], group=None) -> None:
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    _timed("nccl_allreduce_grads", lambda: dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group))
     flat /= ws
     off = 0
     for g in grads:

@@ -138,7 +138,7 @@ class VQBank:
             _lib.check(lib.vqgnn_vq_moments(_lib.ptr(xk), xk.stride(0), _lib.ptr(gk),
                                             gk.stride(0) if joint else 0, B, C, Cg, _lib.ptr(sums), st))
             if self.distributed:   # global batch statistics: every rank whitens identically
-                sums[-1] = float(B)
+                sums[-1:].fill_(float(B))          # a fill kernel (capturable), not a host copy
                 dist.allreduce_sum_(sums, self.process_group)
                 d_count = sums[-1:]
         seed = 1 if (joint and training and not self.bn_inited) else 0
