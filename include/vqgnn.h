@@ -163,15 +163,36 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
  *   vqgnn_mp_fwd_tail: over a CSR holding ONLY tail entries (node = global node id):
  *       y[r]  += sum_e val[e] * feat_scale * O_k[code_k(node[e]), :D]      (y, gq accumulate: run it AFTER
  *       gq[r] += sum_e rval[e] * O_k[code_k(node[e]), D:2D]                 vqgnn_mp_fwd on the in-batch part)
- *       *info += info_scale * sum_r <x[r], gq contribution>               (info must be zero-initialised) */
+ *       *info += info_scale * sum_r <x[r], gq contribution>               (info must be zero-initialised)
+ *   d_nnz != NULL: the entry count lives on the device (vqgnn_plan_v1_build); nnz is then its upper bound. */
 int vqgnn_mp_tail_group(int M, int D, int Wp);
 int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* rows, int64_t n_rows, int64_t N, int G,
                       int16_t* codes_g, void* stream);
 int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* val, const float* rval,
-                      const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* x, int64_t ldx,
-                      const int16_t* codes_g, int64_t N, const float* O, int nb, int M, int D, int Wp,
+                      const int32_t* chunk_row, int chunk, int64_t nnz, const int32_t* d_nnz, int64_t B,
+                      const float* x, int64_t ldx, const int16_t* codes_g, int64_t N, const float* O, int nb, int M, int D, int Wp,
                       float feat_scale, float info_scale, float* y, int64_t ldy, float* gq, int64_t ldgq,
                       float* info, void* ws, void* stream);
+
+/* Device-side, synchronisation-free construction of the v1 batch plan from the reference's batch tuple
+ * (deg_inv, A_BN (r, c, v), A_BB (r, c, v) | None, A_NB_v | None, batch_idx) of
+ * vq_gnn_v1/utils/dataloader.py:64-86 -- what `mapper` (:144-192) rebuilds per branch per layer.
+ *   tail part     (A_BN entries whose column is not a batch node; all of them when bb_r == NULL):
+ *                 t_rowptr [B+1], t_node / t_val / t_rval [nnz] (rv == NULL -> zeros), *t_count = number of tail
+ *                 entries (stays on the device), t_chunk_row [ceil(nnz / tail_chunk)]
+ *   in-batch part (A_BB, + transpose if `symmetric` (GCN, to_symmetric), + self loops deg_inv if `self_loops`,
+ *                 doubled when symmetric): nin = nbb * (1 + symmetric) + self_loops * B entries;
+ *                 forward CSR i_rowptr / i_col / i_val / i_chunk_row and transposed b_rowptr / b_row / b_val /
+ *                 b_chunk_row (chunk rows: ceil(nin / chunk) each)
+ * ws: vqgnn_plan_v1_workspace_bytes(N, B) bytes. */
+size_t vqgnn_plan_v1_workspace_bytes(int64_t N, int64_t B);
+int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, const float* rv, int64_t nnz,
+                        const int64_t* bb_r, const int64_t* bb_c, const float* bb_v, int64_t nbb,
+                        const int64_t* batch_idx, const float* deg_inv, int64_t B, int64_t N, int symmetric,
+                        int self_loops, int tail_chunk, int chunk, int32_t* t_rowptr, int32_t* t_node,
+                        float* t_val, float* t_rval, int32_t* t_count, int32_t* t_chunk_row, int32_t* i_rowptr,
+                        int32_t* i_col, float* i_val, int32_t* i_chunk_row, int32_t* b_rowptr, int32_t* b_row,
+                        float* b_val, int32_t* b_chunk_row, void* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Message passing, GAT, v2 ("B+B'") formulation: OurGATConv.forward/message (vq_gnn_v2/convs.py:165-266)

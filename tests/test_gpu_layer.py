@@ -235,3 +235,36 @@ def test_v1_shared_memory_tail_kernel(conv, C, M, B, E):
     cg = layer.bank.grouped_codes()
     for k in range(layer.bank.nb):
         assert torch.equal(cg[k // G, :, k % G], layer.bank.codes[:, k])
+
+
+@pytest.mark.parametrize("conv,train,recovery", [("SAGE", True, True), ("GCN", True, True), ("GAT", True, True),
+                                                 ("SAGE", False, True), ("GCN", True, False)])
+def test_device_plan_builder_matches_torch_builder(conv, train, recovery):
+    """csrc/plan.cu (vqgnn_plan_v1_build) against the torch builder: same tail / in-batch / transposed structure
+    (as dense matrices: the order inside a row is free), same counts; power-law graph with hub rows."""
+    from vq_gnn_b200 import graph as G
+    dev = torch.device("cuda:0")
+    N, B = 2000, 300
+    g = H.make_graph(N, 60_000, conv, "v1", seed=31, power_law=1.3)
+    bA = H.batch_to(H.make_batch(g, B, "v1", seed=31, train=train, recovery=recovery), dev)
+    p_t = G.plan_from_v1(bA, conv, N, train, dev)
+    p_d = G.plan_from_v1_device(bA, conv, N, train, dev)
+
+    def dense(plan):
+        deg = (plan.fwd_rowptr[1:] - plan.fwd_rowptr[:-1]).long()
+        rows = torch.repeat_interleave(torch.arange(B, device=dev), deg)
+        a = torch.zeros(B, B + N, device=dev, dtype=torch.float64)
+        a.index_put_((rows, plan.fwd_col.long()), plan.fwd_val.double(), accumulate=True)
+        b = torch.zeros(B, B + N, device=dev, dtype=torch.float64)
+        b.index_put_((rows, plan.fwd_col.long()), plan.fwd_rval.double(), accumulate=True)
+        bdeg = (plan.bwd_rowptr[1:] - plan.bwd_rowptr[:-1]).long()
+        bj = torch.repeat_interleave(torch.arange(B, device=dev), bdeg)
+        t = torch.zeros(B, B, device=dev, dtype=torch.float64)
+        t.index_put_((plan.bwd_col.long(), bj), plan.bwd_val.double(), accumulate=True)
+        return a, b, t
+    for x, y in zip(dense(p_t), dense(p_d)):
+        assert torch.equal(x, y)
+    sp = p_d.split_v1()
+    n_tail = int(sp['tail'][6].item())
+    assert n_tail == int((p_t.fwd_col >= B).sum())
+    assert int(sp['tail'][0][-1]) == n_tail and torch.equal(p_t.bwd_rowptr, p_d.bwd_rowptr)

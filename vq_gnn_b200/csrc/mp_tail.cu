@@ -63,8 +63,8 @@ template <int G>
 __global__ void __launch_bounds__(kTailThreads, 1)
     mp_tail_smem_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ node,
                         const float* __restrict__ val, const float* __restrict__ rval,
-                        const int32_t* __restrict__ chunk_row, int n_chunks, int chunk, int nnz, int B,
-                        const int16_t* __restrict__ codes_g, int64_t N, const float* __restrict__ O, int nb, int M,
+                        const int32_t* __restrict__ chunk_row, int n_chunks, int chunk, int nnz,
+                        const int32_t* __restrict__ d_nnz, int B, const int16_t* __restrict__ codes_g, int64_t N, const float* __restrict__ O, int nb, int M,
                         const float* __restrict__ x, int64_t ldx, float feat_scale, float* __restrict__ y,
                         int64_t ldy, float* __restrict__ gq, int64_t ldgq, float* __restrict__ info,
                         float info_scale, double* ws_sum, unsigned int* ws_count, int ng, int cpi,
@@ -75,6 +75,10 @@ __global__ void __launch_bounds__(kTailThreads, 1)
   const uint32_t cb_base = static_cast<uint32_t>(__cvta_generic_to_shared(cb_ptr));
   const int branch_bytes = M * 32;
   __shared__ int next_chunk;  // warps of the CTA draw the item's chunks dynamically
+  if (d_nnz) {  // entry count only known on the device (vqgnn_plan_v1_build): the host sized the grid by an upper bound
+    nnz = __ldg(d_nnz);
+    n_chunks = (nnz + chunk - 1) / chunk;
+  }
   float fpart = 0.f;
   int loaded = -1;
   const int n_items = ng * items_per_group;
@@ -284,8 +288,8 @@ extern "C" int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* ro
 }
 
 extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* val, const float* rval,
-                                 const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* x,
-                                 int64_t ldx, const int16_t* codes_g, int64_t N, const float* O, int nb, int M,
+                                 const int32_t* chunk_row, int chunk, int64_t nnz, const int32_t* d_nnz, int64_t B,
+                                 const float* x, int64_t ldx, const int16_t* codes_g, int64_t N, const float* O, int nb, int M,
                                  int D, int Wp, float feat_scale, float info_scale, float* y, int64_t ldy,
                                  float* gq, int64_t ldgq, float* info, void* ws, void* stream) {
   VQ_CHECK_ARG(rowptr && node && val && rval && x && codes_g && O && y, "mp_fwd_tail: null argument");
@@ -316,7 +320,7 @@ extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, con
     auto kern = mp_tail_smem_kernel<GG>;                                                                      \
     VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     kern<<<std::min(grid, ng * items_per_group), kTailThreads, smem, s>>>(                                    \
-        rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, (int)B, codes_g, N, O, nb, M, x, ldx,  \
+        rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, d_nnz, (int)B, codes_g, N, O, nb, M, x, ldx, \
         feat_scale, y, ldy, gq, ldgq, info, info_scale, ws_sum, ws_count, ng, cpi, items_per_group);          \
   } while (0)
   if (G == 8) VQ_TAIL(8);

@@ -1,0 +1,234 @@
+// Device-side construction of the v1 batch plan from the reference's batch tuple
+//   (deg_inv[B], A_BN (r, c, v) int64/int64/fp32, A_BB (r, c, v) | None, A_NB_v | None, batch_idx[B])
+// (vq_gnn_v1/utils/dataloader.py:64-86; `mapper` :144-192 consumes it once per branch per layer).
+// Entirely asynchronous on the caller's stream -- no host synchronisation, no allocation: the number of tail
+// entries stays on the device (t_count) and the consumers size their grids by the upper bound nnz(A_BN).
+//   tail part     : entries of A_BN whose column is not a batch node, compacted per row (order inside a row is
+//                   irrelevant to the sums), as a CSR over the B rows with global node ids
+//   in-batch part : A_BB (+ its transpose for GCN = to_symmetric, + self loops deg_inv, doubled for GCN), as a CSR
+//                   by row (forward) and by column (backward)
+// HBM-bound integer work: warp-aggregated counting + cursor scatter, two small single-CTA scans.
+#include "common.cuh"
+
+namespace vqgnn {
+
+__global__ void plan_pos_kernel(const int64_t* __restrict__ batch_idx, int B, int32_t* __restrict__ pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) pos[batch_idx[i]] = i;
+}
+
+// one warp-aggregated atomic per distinct key among the flagged lanes; returns the lane's slot
+__device__ __forceinline__ int warp_slot(int* counters, int key, bool flag) {
+  const unsigned active = __ballot_sync(0xffffffffu, flag);
+  int slot = 0;
+  if (flag) {
+    const unsigned peers = __match_any_sync(active, key);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counters + key, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    slot = base + __popc(peers & ((1u << lane) - 1));
+  }
+  return slot;
+}
+
+// pass 1 (count) / pass 2 (scatter) over A_BN
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+    plan_tail_kernel(const int64_t* __restrict__ r, const int64_t* __restrict__ c, const float* __restrict__ v,
+                     const float* __restrict__ rv, int64_t nnz, const int32_t* __restrict__ pos, int has_bb,
+                     int* __restrict__ counters /* count: row_cnt[B]; scatter: cursor[B] */,
+                     const int32_t* __restrict__ t_rowptr, int32_t* __restrict__ t_node,
+                     float* __restrict__ t_val, float* __restrict__ t_rval) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n_round = (nnz + 31) / 32 * 32;  // keep warps converged for the warp-wide intrinsics
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_round; e += stride) {
+    bool tail = false;
+    int row = 0;
+    int64_t col = 0;
+    if (e < nnz) {
+      col = c[e];
+      row = static_cast<int>(r[e]);
+      tail = !has_bb || __ldg(pos + col) < 0;
+    }
+    const int slot = warp_slot(counters, row, tail);
+    if (SCATTER && tail) {
+      const int64_t dst = static_cast<int64_t>(__ldg(t_rowptr + row)) + slot;
+      t_node[dst] = static_cast<int32_t>(col);
+      t_val[dst] = v[e];
+      t_rval[dst] = rv ? rv[e] : 0.f;
+    }
+  }
+}
+
+// in-batch entries: A_BB (+ transposes) + self loops.  KEY 0: by row (forward CSR), 1: by column (transposed)
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+    plan_inb_kernel(const int64_t* __restrict__ br, const int64_t* __restrict__ bc, const float* __restrict__ bv,
+                    int64_t nbb, const float* __restrict__ deg_inv, int B, int symmetric, int self_loops,
+                    int* __restrict__ cnt_row, int* __restrict__ cnt_col, const int32_t* __restrict__ i_rowptr,
+                    int32_t* __restrict__ i_col, float* __restrict__ i_val, const int32_t* __restrict__ b_rowptr,
+                    int32_t* __restrict__ b_row, float* __restrict__ b_val) {
+  const int64_t total = nbb * (symmetric ? 2 : 1) + (self_loops ? B : 0);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+    int row, col;
+    float val;
+    if (t < nbb) {
+      row = static_cast<int>(br[t]), col = static_cast<int>(bc[t]), val = bv[t];
+    } else if (symmetric && t < 2 * nbb) {
+      row = static_cast<int>(bc[t - nbb]), col = static_cast<int>(br[t - nbb]), val = bv[t - nbb];
+    } else {
+      row = col = static_cast<int>(t - nbb * (symmetric ? 2 : 1));
+      val = deg_inv[row] * (symmetric ? 2.f : 1.f);  // to_symmetric() doubles the diagonal (dataloader.py:189-190)
+    }
+    const int s_row = atomicAdd(cnt_row + row, 1);
+    const int s_col = atomicAdd(cnt_col + col, 1);
+    if (SCATTER) {
+      const int d0 = i_rowptr[row] + s_row;
+      i_col[d0] = col, i_val[d0] = val;
+      const int d1 = b_rowptr[col] + s_col;
+      b_row[d1] = row, b_val[d1] = val;
+    }
+  }
+}
+
+// exclusive scan of cnt[0..n) into ptr[0..n] by one CTA; zeroes cnt for reuse as cursors; optional total out
+__global__ void __launch_bounds__(1024) plan_scan_kernel(int* __restrict__ cnt, int n, int32_t* __restrict__ ptr,
+                                                         int32_t* __restrict__ total) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int x = i < n ? cnt[i] : 0;
+    int s = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += y;
+    }
+    if (lane == 31) warp_tot[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    const int before = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + s - x;
+    if (i < n) ptr[i] = before, cnt[i] = 0;
+    __syncthreads();
+    if (tid == 1023) carry = before + x;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    ptr[n] = carry;
+    if (total) *total = carry;
+  }
+}
+
+// chunk_row for a CSR whose nnz is only known on the device
+__global__ void plan_chunk_rows_dev_kernel(const int32_t* __restrict__ rowptr, int R, const int32_t* __restrict__ d_nnz,
+                                           int chunk, int max_chunks, int32_t* __restrict__ chunk_row) {
+  const int cI = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cI >= max_chunks) return;
+  const int64_t e = static_cast<int64_t>(cI) * chunk;
+  if (e >= *d_nnz) {
+    chunk_row[cI] = R - 1;
+    return;
+  }
+  int lo = 0, hi = R;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(rowptr + mid) <= e) lo = mid;
+    else hi = mid;
+  }
+  chunk_row[cI] = lo;
+}
+
+static int plan_grid(int64_t n) { return static_cast<int>(std::min<int64_t>((n + 255) / 256, 16 * kNumSMs)); }
+
+}  // namespace vqgnn
+
+using namespace vqgnn;
+
+extern "C" size_t vqgnn_plan_v1_workspace_bytes(int64_t N, int64_t B) {
+  return static_cast<size_t>(N) * 4 + static_cast<size_t>(B) * 4 * 3 + 64;
+}
+
+extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, const float* rv, int64_t nnz,
+                                   const int64_t* bb_r, const int64_t* bb_c, const float* bb_v, int64_t nbb,
+                                   const int64_t* batch_idx, const float* deg_inv, int64_t B, int64_t N,
+                                   int symmetric, int self_loops, int tail_chunk, int chunk, int32_t* t_rowptr,
+                                   int32_t* t_node, float* t_val, float* t_rval, int32_t* t_count,
+                                   int32_t* t_chunk_row, int32_t* i_rowptr, int32_t* i_col, float* i_val,
+                                   int32_t* i_chunk_row, int32_t* b_rowptr, int32_t* b_row, float* b_val,
+                                   int32_t* b_chunk_row, void* ws, void* stream) {
+  VQ_CHECK_ARG(r && c && v && batch_idx && t_rowptr && t_node && t_val && t_rval && t_count && t_chunk_row && i_rowptr &&
+                   b_rowptr && ws,
+               "plan_v1_build: null argument");
+  VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && N > 0 && N < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31) && nbb >= 0,
+               "plan_v1_build: sizes must fit int32");
+  VQ_CHECK_ARG(nbb == 0 || (bb_r && bb_c && bb_v), "plan_v1_build: A_BB arrays missing");
+  VQ_CHECK_ARG(!self_loops || deg_inv, "plan_v1_build: self loops need deg_inv");
+  VQ_CHECK_ARG(tail_chunk > 0 && tail_chunk % 32 == 0 && chunk > 0 && chunk % 32 == 0, "plan_v1_build: bad chunk sizes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int32_t* pos = static_cast<int32_t*>(ws);
+  int* cnt_t = reinterpret_cast<int*>(pos + N);
+  int* cnt_r = cnt_t + B;
+  int* cnt_c = cnt_r + B;
+  const int has_bb = bb_r != nullptr;   // A_BB == None (eval / no recovery): every neighbour goes through its codeword
+  if (has_bb) {
+    VQ_CUDA(cudaMemsetAsync(pos, 0xFF, sizeof(int32_t) * N, s));
+    plan_pos_kernel<<<ceil_div(B, 256), 256, 0, s>>>(batch_idx, (int)B, pos);
+    VQ_LAUNCH_CHECK();
+  }
+  VQ_CUDA(cudaMemsetAsync(cnt_t, 0, sizeof(int) * B * 3, s));
+  // ---- tail part
+  const int tgrid = plan_grid(nnz);
+  if (nnz > 0) {
+    plan_tail_kernel<false><<<tgrid, 256, 0, s>>>(r, c, v, rv, nnz, pos, has_bb, cnt_t, nullptr, nullptr, nullptr, nullptr);
+    VQ_LAUNCH_CHECK();
+  }
+  plan_scan_kernel<<<1, 1024, 0, s>>>(cnt_t, (int)B, t_rowptr, t_count);
+  VQ_LAUNCH_CHECK();
+  if (nnz > 0) {
+    plan_tail_kernel<true><<<tgrid, 256, 0, s>>>(r, c, v, rv, nnz, pos, has_bb, cnt_t, t_rowptr, t_node, t_val, t_rval);
+    VQ_LAUNCH_CHECK();
+  }
+  const int max_chunks = static_cast<int>((nnz + tail_chunk - 1) / tail_chunk);
+  if (max_chunks > 0) {
+    plan_chunk_rows_dev_kernel<<<ceil_div(max_chunks, 256), 256, 0, s>>>(t_rowptr, (int)B, t_count, tail_chunk,
+                                                                        max_chunks, t_chunk_row);
+    VQ_LAUNCH_CHECK();
+  }
+  // ---- in-batch part (forward by row, backward by column)
+  const int64_t nin = nbb * (symmetric ? 2 : 1) + (self_loops ? B : 0);
+  if (nin > 0) {
+    VQ_CHECK_ARG(i_col && i_val && b_row && b_val, "plan_v1_build: in-batch outputs missing");
+    const int igrid = plan_grid(nin);
+    plan_inb_kernel<false><<<igrid, 256, 0, s>>>(bb_r, bb_c, bb_v, nbb, deg_inv, (int)B, symmetric, self_loops, cnt_r,
+                                                 cnt_c, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    VQ_LAUNCH_CHECK();
+  }
+  plan_scan_kernel<<<1, 1024, 0, s>>>(cnt_r, (int)B, i_rowptr, nullptr);
+  VQ_LAUNCH_CHECK();
+  plan_scan_kernel<<<1, 1024, 0, s>>>(cnt_c, (int)B, b_rowptr, nullptr);
+  VQ_LAUNCH_CHECK();
+  if (nin > 0) {
+    plan_inb_kernel<true><<<plan_grid(nin), 256, 0, s>>>(bb_r, bb_c, bb_v, nbb, deg_inv, (int)B, symmetric, self_loops,
+                                                         cnt_r, cnt_c, i_rowptr, i_col, i_val, b_rowptr, b_row, b_val);
+    VQ_LAUNCH_CHECK();
+    if (int rc = vqgnn_mp_chunk_rows(i_rowptr, B, nin, chunk, i_chunk_row, stream)) return rc;
+    if (int rc = vqgnn_mp_chunk_rows(b_rowptr, B, nin, chunk, b_chunk_row, stream)) return rc;
+  }
+  return VQGNN_OK;
+}

@@ -100,7 +100,7 @@ class VQGAT1Function(torch.autograd.Function):
                                          float(wu), _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r),
                                          _lib.ptr(cs), _lib.ptr(stat), st))
         y, den = torch.empty(B, C, device=dev), torch.empty(B, nb, device=dev)
-        need_info = plan.training and plan.fwd_rval is not None
+        need_info = plan.training and plan.has_rval
         info = torch.zeros((), device=dev)
         ws = torch.empty(8, dtype=torch.float64, device=dev) if need_info else None
         _lib.check(lib.vqgnn_gat1_fwd(
@@ -121,7 +121,7 @@ class VQGAT1Function(torch.autograd.Function):
         bank = layer.bank
         B, C = x.shape
         nb, M, dev = bank.nb, bank.M, x.device
-        if plan.fwd_rval is None:
+        if not plan.has_rval:
             raise RuntimeError("the v1 GAT backward needs a training plan (reverse values A_NB_v)")
         dy = dy.contiguous().float()
         dinfo = dinfo.contiguous().float()

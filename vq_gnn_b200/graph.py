@@ -21,7 +21,6 @@ vq_gnn_v1/utils/dataloader.py:144-192) and covers both formulations with one lay
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
 from typing import Optional, Tuple
 
 import torch
@@ -89,34 +88,72 @@ class CSRAdj:
         return out.index_put_((row, col), val, accumulate=True)
 
 
-@dataclass
 class BatchPlan:
-    version: str
-    conv_type: str
-    B: int
-    R: int                       # forward output rows
-    T: int                       # number of tail entries (v2: B'; v1: N, identity)
-    N: int
-    batch_idx: Tensor            # int32 [B]  global node ids of the batch rows
-    fwd_rowptr: Tensor           # int32 [R+1]
-    fwd_col: Tensor              # int32 [nnz]
-    fwd_val: Tensor              # fp32  [nnz]
-    fwd_rval: Optional[Tensor]   # fp32  [nnz] reverse values (v1) or None
-    tail_node: Optional[Tensor]  # int32 [T] or None (identity)
-    bwd_rowptr: Tensor           # int32 [B+1]
-    bwd_col: Tensor              # int32 [nnzT]   source row ids (< R)
-    bwd_val: Tensor              # fp32  [nnzT]
-    bwd_eid: Optional[Tensor] = None  # int32 [nnzT] position of the same entry in the forward CSR (GAT)
-    training: bool = True
-    extras: dict = field(default_factory=dict)
+    """Kernel-ready description of one mini-batch graph (see the module docstring).
+
+    The merged forward CSR (`fwd_rowptr / fwd_col / fwd_val / fwd_rval`) may be LAZY: the v1 builder produces
+    the in-batch / tail split that the fast kernels consume directly and only sorts the merged form when some
+    consumer asks for it (generic kernel, GAT, tests)."""
+
+    def __init__(self, version: str, conv_type: str, B: int, R: int, T: int, N: int, batch_idx: Tensor,
+                 fwd_rowptr: Optional[Tensor], fwd_col: Optional[Tensor], fwd_val: Optional[Tensor],
+                 fwd_rval: Optional[Tensor], tail_node: Optional[Tensor], bwd_rowptr: Tensor, bwd_col: Tensor,
+                 bwd_val: Tensor, bwd_eid: Optional[Tensor] = None, training: bool = True,
+                 extras: Optional[dict] = None, merged_builder=None, nnz: Optional[int] = None,
+                 has_rval: Optional[bool] = None):
+        self.version, self.conv_type = version, conv_type
+        self.B, self.R, self.T, self.N = B, R, T, N
+        self.batch_idx = batch_idx             # int32 [B]  global node ids of the batch rows
+        self._fwd = None if fwd_rowptr is None else (fwd_rowptr, fwd_col, fwd_val, fwd_rval)
+        self._merged_builder = merged_builder  # () -> (rowptr int32 [R+1], col int32, val fp32, rval fp32 | None)
+        self.tail_node = tail_node             # int32 [T] or None (identity)
+        self.bwd_rowptr, self.bwd_col, self.bwd_val, self.bwd_eid = bwd_rowptr, bwd_col, bwd_val, bwd_eid
+        self.training = training
+        self.extras = {} if extras is None else extras
+        self._nnz = nnz
+        self._has_rval = has_rval
+
+    def _merged(self):
+        if self._fwd is None:
+            self._fwd = self._merged_builder()
+            self._nnz = int(self._fwd[1].numel())     # exact from now on (a device-built plan only had a bound)
+            self.extras.pop('chunk_rows_fwd', None)
+        return self._fwd
+
+    fwd_rowptr = property(lambda self: self._merged()[0])   # int32 [R+1]
+    fwd_col = property(lambda self: self._merged()[1])      # int32 [nnz]: < B dense row, >= B tail entry
+    fwd_val = property(lambda self: self._merged()[2])      # fp32  [nnz]
+    fwd_rval = property(lambda self: self._merged()[3])     # fp32  [nnz] reverse values (v1) or None
+
+    @property
+    def has_rval(self) -> bool:
+        return self._has_rval if self._has_rval is not None else self.fwd_rval is not None
 
     @property
     def device(self):
-        return self.fwd_col.device
+        return self.bwd_rowptr.device
 
     @property
     def nnz(self) -> int:
-        return int(self.fwd_col.numel())
+        return self._nnz if self._nnz is not None else int(self.fwd_col.numel())
+
+    def tensors(self):
+        """Every tensor the plan currently holds (for stream bookkeeping)."""
+        out = [self.batch_idx, self.tail_node, self.bwd_rowptr, self.bwd_col, self.bwd_val, self.bwd_eid]
+        if self._fwd is not None:
+            out += list(self._fwd)
+
+        def rec(o):
+            if isinstance(o, torch.Tensor):
+                out.append(o)
+            elif isinstance(o, (tuple, list)):
+                for u in o:
+                    rec(u)
+            elif isinstance(o, dict):
+                for u in o.values():
+                    rec(u)
+        rec(self.extras)
+        return [t for t in out if isinstance(t, torch.Tensor)]
 
     def chunk_rows(self, which: str) -> Tensor:
         """nnz-balanced work partition of the forward ('fwd') or transposed ('bwd') CSR for the CUDA
@@ -125,8 +162,11 @@ class BatchPlan:
         t = self.extras.get(key)
         if t is None:
             from . import _lib
-            rowptr, nnz, rows = ((self.fwd_rowptr, self.nnz, self.R) if which == 'fwd'
-                                 else (self.bwd_rowptr, int(self.bwd_col.numel()), self.B))
+            if which == 'fwd':
+                rowptr = self.fwd_rowptr          # materialises a lazy merged CSR (and makes nnz exact) first
+                nnz, rows = self.nnz, self.R
+            else:
+                rowptr, nnz, rows = self.bwd_rowptr, int(self.bwd_col.numel()), self.B
             _lib.require_device(rowptr)
             lib = _lib.load()
             n = int(lib.vqgnn_mp_num_chunks(nnz, MP_CHUNK))
@@ -139,44 +179,51 @@ class BatchPlan:
         """Build every lazily-derived piece now (on the current stream): the work partitions and, for v1
         plans with long rows, the in-batch / tail split.  `LowRankGNN.prepare` calls this so that a prefetching
         loader pays for it (and its host syncs) off the training stream."""
-        self.chunk_rows('fwd')
         self.chunk_rows('bwd')
-        if (split and self.version == 'v1' and self.fwd_rval is not None
+        if (split and self.version == 'v1' and self.has_rval and self.conv_type != 'GAT'
                 and self.nnz >= TAIL_MIN_AVG_DEGREE * self.B):
             self.split_v1()
+        else:
+            self.chunk_rows('fwd')
         return self
 
     def split_v1(self):
         """v1 plans: the forward CSR split into its in-batch part (dense rows, generic kernel) and its tail
-        part (out-of-batch neighbours, shared-memory codebook kernel).  Built lazily, once per plan.
+        part (out-of-batch neighbours, shared-memory codebook kernel).  Built once per plan.
         -> dict(inb=(rowptr, col, val, chunk_row, nnz), tail=(rowptr, node, val, rval, chunk_row, nnz))"""
         sp = self.extras.get('split')
         if sp is None:
             from . import _lib
-            assert self.version == 'v1' and self.fwd_rval is not None
+            assert self.version == 'v1' and self.has_rval
             lib = _lib.load()
-            dev = self.fwd_col.device
             B = self.B
-            deg = (self.fwd_rowptr[1:] - self.fwd_rowptr[:-1]).long()
-            rows = torch.repeat_interleave(torch.arange(B, device=dev), deg)
-            is_tail = self.fwd_col >= B
 
-            def csr(mask, chunk):
-                r = rows[mask]
-                ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-                ptr[1:] = torch.cumsum(torch.bincount(r, minlength=B), 0).to(torch.int32)
-                nnz = int(r.numel())
+            def chunks(ptr, nnz, chunk):
                 n = int(lib.vqgnn_mp_num_chunks(nnz, chunk))
-                cr = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+                cr = torch.empty(max(n, 1), dtype=torch.int32, device=ptr.device)
                 _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(ptr), B, nnz, chunk, _lib.ptr(cr), _lib.stream()))
-                return ptr, cr, nnz
+                return cr
 
-            tptr, tcr, tnnz = csr(is_tail, TAIL_CHUNK)
-            iptr, icr, innz = csr(~is_tail, MP_CHUNK)
-            sp = dict(
-                tail=(tptr, (self.fwd_col[is_tail] - B).contiguous(), self.fwd_val[is_tail].contiguous(),
-                      self.fwd_rval[is_tail].contiguous(), tcr, tnnz),
-                inb=(iptr, self.fwd_col[~is_tail].contiguous(), self.fwd_val[~is_tail].contiguous(), icr, innz))
+            raw = self.extras.get('split_raw')
+            if raw is None:      # derive from the merged CSR
+                dev = self.fwd_col.device
+                deg = (self.fwd_rowptr[1:] - self.fwd_rowptr[:-1]).long()
+                rows = torch.repeat_interleave(torch.arange(B, device=dev), deg)
+                is_tail = self.fwd_col >= B
+
+                def ptr_of(mask):
+                    ptr = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+                    ptr[1:] = torch.cumsum(torch.bincount(rows[mask], minlength=B), 0).to(torch.int32)
+                    return ptr
+                raw = dict(tail=(ptr_of(is_tail), (self.fwd_col[is_tail] - B).contiguous(),
+                                 self.fwd_val[is_tail].contiguous(), self.fwd_rval[is_tail].contiguous()),
+                           inb=(ptr_of(~is_tail), self.fwd_col[~is_tail].contiguous(),
+                                self.fwd_val[~is_tail].contiguous()))
+            tptr, tnode, tval, trval = raw['tail']
+            iptr, icol, ival = raw['inb']
+            tn, inn = int(tnode.numel()), int(icol.numel())
+            sp = dict(tail=(tptr, tnode, tval, trval, chunks(tptr, tn, TAIL_CHUNK), tn),
+                      inb=(iptr, icol, ival, chunks(iptr, inn, MP_CHUNK), inn))
             self.extras['split'] = sp
         return sp
 
@@ -184,6 +231,7 @@ class BatchPlan:
 MP_CHUNK = 256   # CSR entries per warp task (multiple of 32)
 
 
+DEVICE_PLAN_BUILDER = True   # v1 plans on CUDA are built by csrc/plan.cu (False: the torch builder below)
 TAIL_CHUNK = 512  # entries per warp task of the shared-memory tail kernel (csrc/mp_tail.cu)
 TAIL_MIN_AVG_DEGREE = 32   # below this the per-row reduce of the lane=entry kernel does not pay
 
@@ -224,6 +272,79 @@ def plan_from_v2(batch_A, conv_type: str, N: int, training: bool, device) -> Bat
                      bptr, bcol, bval, beid, training)
 
 
+def _csr_ptr(rows: Tensor, n: int) -> Tensor:
+    ptr = torch.zeros(n + 1, dtype=torch.int32, device=rows.device)
+    if rows.numel() > 0:
+        ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=n), 0).to(torch.int32)
+    return ptr
+
+
+def plan_from_v1_device(batch_A, conv_type: str, N: int, training: bool, device) -> BatchPlan:
+    """`plan_from_v1` built by libvqgnn on the device (csrc/plan.cu: vqgnn_plan_v1_build): no host
+    synchronisation and no torch sort/mask ops, so a loader can enqueue it behind the H2D copy of the batch on a
+    side stream from the training thread itself.  The number of tail entries stays on the device."""
+    from . import _lib
+    deg_inv, A_BN, A_BB, A_NB_v, batch_idx = batch_A
+    lib, st = _lib.load(), _lib.stream()
+    dev = torch.device(device)
+    B = int(batch_idx.shape[0])
+    r, c, v = (t.to(dev) for t in A_BN)
+    r, c, v = r.long().contiguous(), c.long().contiguous(), v.float().contiguous()
+    _lib.require_device(v)
+    nnz = int(r.numel())
+    if conv_type == 'GCN':
+        rv = v
+    elif A_NB_v is not None:
+        rv = A_NB_v.to(dev).float().contiguous()
+    else:
+        rv = None
+    if A_BB is not None:
+        br, bc, bv = (t.to(dev) for t in A_BB)
+        br, bc, bv = br.long().contiguous(), bc.long().contiguous(), bv.float().contiguous()
+        nbb = int(br.numel())
+        if nbb == 0:   # keep the "A_BB present" semantics with valid (non-NULL) pointers
+            br = bc = torch.zeros(1, dtype=torch.long, device=dev)
+            bv = torch.zeros(1, device=dev)
+    else:
+        br = bc = bv = None
+        nbb = 0
+    sym, loops = int(conv_type == 'GCN'), int(conv_type != 'SAGE')
+    nin = nbb * (1 + sym) + loops * B
+    bidx = batch_idx.to(dev).long().contiguous()
+    dinv = deg_inv.to(dev).float().contiguous()
+    i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    f32 = lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    n_tc = int(lib.vqgnn_mp_num_chunks(nnz, TAIL_CHUNK))
+    n_ic = int(lib.vqgnn_mp_num_chunks(nin, MP_CHUNK))
+    tptr, tnode, tval, trval, tcount, tcr = i32(B + 1), i32(nnz), f32(nnz), f32(nnz), i32(1), i32(n_tc)
+    iptr, icol, ival, icr = i32(B + 1), i32(nin), f32(nin), i32(n_ic)
+    bptr, brow, bval, bcr = i32(B + 1), i32(nin), f32(nin), i32(n_ic)
+    ws = torch.empty(int(lib.vqgnn_plan_v1_workspace_bytes(N, B)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.vqgnn_plan_v1_build(
+        _lib.ptr(r), _lib.ptr(c), _lib.ptr(v), _lib.ptr(rv), nnz, _lib.ptr(br), _lib.ptr(bc), _lib.ptr(bv), nbb,
+        _lib.ptr(bidx), _lib.ptr(dinv), B, N, sym, loops, TAIL_CHUNK, MP_CHUNK,
+        _lib.ptr(tptr), _lib.ptr(tnode), _lib.ptr(tval), _lib.ptr(trval), _lib.ptr(tcount), _lib.ptr(tcr),
+        _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), _lib.ptr(icr),
+        _lib.ptr(bptr), _lib.ptr(brow), _lib.ptr(bval), _lib.ptr(bcr), _lib.ptr(ws), st))
+
+    def merged():   # generic-kernel / GAT / test consumers: needs the tail count on the host
+        nt = int(tcount.item())
+        rows_t = torch.repeat_interleave(torch.arange(B, device=dev), (tptr[1:] - tptr[:-1]).long())
+        rows_i = torch.repeat_interleave(torch.arange(B, device=dev), (iptr[1:] - iptr[:-1]).long())
+        mr = torch.cat([rows_t, rows_i])
+        mc = torch.cat([tnode[:nt].long() + B, icol[:nin].long()])
+        order = torch.argsort(mr * (B + N) + mc, stable=True)
+        mv = torch.cat([tval[:nt], ival[:nin]])[order]
+        mrv = torch.cat([trval[:nt], torch.zeros(nin, device=dev)])[order]
+        return _csr_ptr(mr, B), _i32(mc[order]), mv.contiguous(), mrv.contiguous()
+
+    extras = {'split': dict(tail=(tptr, tnode, tval, trval, tcr, nnz, tcount),
+                            inb=(iptr, icol[:nin], ival[:nin], icr, nin)),
+              'chunk_rows_bwd': bcr, '_keep': (r, c, v, rv, br, bc, bv, bidx, dinv, ws)}
+    return BatchPlan('v1', conv_type, B, B, N, N, _i32(bidx), None, None, None, None, None, bptr, brow[:nin],
+                     bval[:nin], None, training, extras=extras, merged_builder=merged, nnz=nnz + nin, has_rval=True)
+
+
 def plan_from_v1(batch_A, conv_type: str, N: int, training: bool, device) -> BatchPlan:
     """batch_A = (deg_inv[B], A_BN(r,c,v), A_BB(r,c,v)|None, A_NB_v|None, batch_idx[B])
     (vq_gnn_v1/utils/dataloader.py:86, mapper :144-192).
@@ -231,7 +352,10 @@ def plan_from_v1(batch_A, conv_type: str, N: int, training: bool, device) -> Bat
     Assumes, as the reference's loader guarantees (dataloader.py:69-73), that A_BB is the restriction
     of A_BN to in-batch columns with the same values; then mapper's "+v on the codeword column, -v
     cancellation, drop <= 0" (:149-180) is exactly "out-of-batch entries only", which is what is built.
-    """
+
+    Produced directly in split form -- tail entries (a stable compaction of A_BN, no sort) and the small in-batch
+    block (A_BB, + its transpose for GCN, + self loops) -- because that is what the fast kernels read; the merged,
+    (row, col)-sorted CSR is assembled lazily for the consumers that want it."""
     deg_inv, A_BN, A_BB, A_NB_v, batch_idx = batch_A
     B = int(batch_idx.shape[0])
     dev = device
@@ -244,32 +368,52 @@ def plan_from_v1(batch_A, conv_type: str, N: int, training: bool, device) -> Bat
         rv = A_NB_v.to(dev).float()              # (:153-154)
     else:
         rv = torch.zeros_like(v)                 # eval: no reverse block
-    rows, cols, vals, rvals = [], [], [], []
+    # ---- tail part ---------------------------------------------------------------------------------
     if A_BB is not None:
         pos = torch.full((N,), -1, dtype=torch.long, device=dev)
         pos[batch_idx] = torch.arange(B, device=dev)
         out = pos[c] < 0
-        rows.append(r[out]), cols.append(c[out] + B), vals.append(v[out]), rvals.append(rv[out])
+        tr, tc, tv, trv = r[out], c[out], v[out], rv[out]
+    else:
+        tr, tc, tv, trv = r, c, v, rv
+    if tr.numel() > 1 and not bool((tr[1:] >= tr[:-1]).all()):   # the reference's loader emits row-sorted COO
+        order = torch.argsort(tr, stable=True)
+        tr, tc, tv, trv = tr[order], tc[order], tv[order], trv[order]
+    tail = (_csr_ptr(tr, B), _i32(tc), tv.contiguous(), trv.contiguous())
+    # ---- in-batch part (small) -----------------------------------------------------------------------
+    rows, cols, vals = [], [], []
+    if A_BB is not None:
         br, bc, bv = (t.to(dev) for t in A_BB)
         br, bc, bv = br.long(), bc.long(), bv.float()
         if conv_type == 'GCN':                   # S + S^T on the in-batch block
             br, bc, bv = torch.cat([br, bc]), torch.cat([bc, br]), torch.cat([bv, bv])
-        rows.append(br), cols.append(bc), vals.append(bv), rvals.append(torch.zeros_like(bv))
-    else:
-        rows.append(r), cols.append(c + B), vals.append(v), rvals.append(rv)
+        rows.append(br), cols.append(bc), vals.append(bv)
     if conv_type != 'SAGE':                      # self loops, value deg_inv (:182-185); doubled by to_symmetric
         d = torch.arange(B, device=dev)
-        dv = deg_inv.to(dev).float() * (2.0 if conv_type == 'GCN' else 1.0)
-        rows.append(d), cols.append(d), vals.append(dv), rvals.append(torch.zeros_like(dv))
-    rows, cols = torch.cat(rows), torch.cat(cols)
-    vals, rvals = torch.cat(vals), torch.cat(rvals)
-    order = torch.argsort(rows * (B + N) + cols, stable=True)
-    rows, cols, vals, rvals = rows[order], cols[order], vals[order], rvals[order]
-    rowptr = torch.zeros(B + 1, dtype=torch.long, device=dev)
-    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=B), 0)
-    bptr, bcol, bval, beid = _transpose_lt(rows, cols, vals, B)
-    return BatchPlan('v1', conv_type, B, B, N, N, _i32(batch_idx), _i32(rowptr), _i32(cols),
-                     vals.contiguous(), rvals.contiguous(), None, bptr, bcol, bval, beid, training)
+        rows.append(d), cols.append(d)
+        vals.append(deg_inv.to(dev).float() * (2.0 if conv_type == 'GCN' else 1.0))
+    if rows:
+        ir, ic, iv = torch.cat(rows), torch.cat(cols), torch.cat(vals)
+        order = torch.argsort(ir * B + ic, stable=True)
+        ir, ic, iv = ir[order], ic[order], iv[order]
+    else:
+        ir = ic = torch.zeros(0, dtype=torch.long, device=dev)
+        iv = torch.zeros(0, device=dev)
+    inb = (_csr_ptr(ir, B), _i32(ic), iv.contiguous())
+    bptr, bcol, bval, _ = _transpose_lt(ir, ic, iv, B)
+    nnz = int(tc.numel() + ic.numel())
+
+    def merged():
+        mr = torch.cat([tr, ir])
+        mc = torch.cat([tc + B, ic])
+        order = torch.argsort(mr * (B + N) + mc, stable=True)
+        mv = torch.cat([tv, iv])[order]
+        mrv = torch.cat([trv, torch.zeros_like(iv)])[order]
+        return _csr_ptr(mr, B), _i32(mc[order]), mv.contiguous(), mrv.contiguous()
+
+    return BatchPlan('v1', conv_type, B, B, N, N, _i32(batch_idx), None, None, None, None, None, bptr, bcol, bval,
+                     None, training, extras={'split_raw': dict(tail=tail, inb=inb)}, merged_builder=merged,
+                     nnz=nnz, has_rval=True)
 
 
 def build_plan(batch_A, conv_type: str, N: int, training: bool, device) -> BatchPlan:
@@ -278,6 +422,8 @@ def build_plan(batch_A, conv_type: str, N: int, training: bool, device) -> Batch
     if len(batch_A) == 3:
         return plan_from_v2(batch_A, conv_type, N, training, device)
     if len(batch_A) == 5:
+        if torch.device(device).type == 'cuda' and DEVICE_PLAN_BUILDER:
+            return plan_from_v1_device(batch_A, conv_type, N, training, device)
         return plan_from_v1(batch_A, conv_type, N, training, device)
     raise ValueError("batch_A must be the v2 (batch_idx, subset, adj) or the v1 "
                      "(deg_inv, A_BN, A_BB, A_NB_v, batch_idx) tuple")

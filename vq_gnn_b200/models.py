@@ -71,7 +71,7 @@ class VQConvFunction(torch.autograd.Function):
         need_info = plan.training
         info = torch.zeros((), device=dev)
         v1 = plan.version == 'v1'
-        gq = torch.empty(B, C, device=dev) if (v1 and plan.fwd_rval is not None) else None
+        gq = torch.empty(B, C, device=dev) if (v1 and plan.has_rval) else None
         ws = _mp_ws(dev) if need_info else None
         codes_g = None
         if v1 and gq is not None and layer.use_tail_kernel and (
@@ -82,7 +82,8 @@ class VQConvFunction(torch.autograd.Function):
             # through the shared-memory codebook kernel, which accumulates on top (csrc/mp_tail.cu)
             sp = plan.split_v1()
             iptr, icol, ival, icr, innz = sp['inb']
-            tptr, tnode, tval, trval, tcr, tnnz = sp['tail']
+            tptr, tnode, tval, trval, tcr, tnnz = sp['tail'][:6]
+            tcount = sp['tail'][6] if len(sp['tail']) > 6 else None   # entry count on the device (plan.cu)
             _lib.check(lib.vqgnn_mp_fwd(
                 _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), None, _lib.ptr(icr), MP_CHUNK, innz, B, B,
                 _lib.ptr(x), x.stride(0), None, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
@@ -90,7 +91,7 @@ class VQConvFunction(torch.autograd.Function):
             gq.zero_()
             _lib.check(lib.vqgnn_mp_fwd_tail(
                 _lib.ptr(tptr), _lib.ptr(tnode), _lib.ptr(tval), _lib.ptr(trval), _lib.ptr(tcr), TAIL_CHUNK, tnnz,
-                B, _lib.ptr(x), x.stride(0), _lib.ptr(codes_g), codes_g.shape[1], _lib.ptr(bank.O), bank.nb,
+                _lib.ptr(tcount), B, _lib.ptr(x), x.stride(0), _lib.ptr(codes_g), codes_g.shape[1], _lib.ptr(bank.O), bank.nb,
                 bank.M, bank.D, bank.Wp, float(wu), float(wu), _lib.ptr(y), y.stride(0), _lib.ptr(gq),
                 gq.stride(0), _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
         else:
@@ -389,7 +390,7 @@ class LowRankGNN(nn.Module):
         """Build the kernel plan once per mini-batch (shared by all layers)."""
         device = device or next(self.parameters()).device
         plan = build_plan(batch_A, self.conv_type, self.num_N, self.training, device)
-        return plan.warm() if plan.fwd_col.is_cuda else plan
+        return plan.warm() if plan.bwd_col.is_cuda else plan
 
     def forward(self, batch, warm_up_rate=1, unlabeled=False):
         losses_full, info_backwards_full = 0, 0
