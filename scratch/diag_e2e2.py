@@ -13,15 +13,11 @@ for x, bA, y in batches:
 import threading
 LOG = []
 def prep(b):
-    t0 = time.perf_counter()
-    torch.cuda.current_stream().synchronize()      # H2D done
     t1 = time.perf_counter()
     x, bA, y = b
     p = model.prepare(bA)
     t2 = time.perf_counter()
-    torch.cuda.current_stream().synchronize()
-    t3 = time.perf_counter()
-    LOG.append(f"  worker: h2d-wait {1e3*(t1-t0):.2f} prepare(cpu) {1e3*(t2-t1):.2f} prepare(gpu tail) {1e3*(t3-t2):.2f}")
+    LOG.append(f"  prepare(cpu) {1e3*(t2-t1):.2f}")
     return x, p, y
 side = torch.cuda.Stream(device=dev)
 def run(n, verbose):
@@ -34,6 +30,7 @@ def run(n, verbose):
         t2 = time.perf_counter()
         l = float(loss.item())
         t3 = time.perf_counter()
+        if verbose: print(f"  cudaMallocs so far {torch.cuda.memory_stats()['num_device_alloc']}", end=" ")
         if verbose: print(f"step {i}: wait {1e3*(t1-t0):.2f} launch {1e3*(t2-t1):.2f} sync {1e3*(t3-t2):.2f} ms")
     pf.drain()
 run(5, False)
