@@ -263,7 +263,8 @@ def main():
                           "num-M 1024, num-D 4, batch 6000, cont sampler walk 3, 3 layers (604->128->128->41)",
               "step": "3-layer fwd + CE loss + bwd (VQ assign + EMA update of every layer inside bwd) + RMSprop",
               "value_formula": "B * num_layers / t_step", "batch_nodes": c["B"], "num_layers": c["layers"],
-              "parallelism": f"dp{world} (node-partitioned batches; EMA stats + weight grads allreduced)",
+              "parallelism": f"dp{world} (node-partitioned batches; whitening moments + EMA stats + weight grads "
+                             "allreduced, code-table updates all-gathered)",
               "l2": "4 distinct batches rotated AND a 256 MiB L2 flush between timed steps",
               "launch": "one CUDA graph per resident batch (whole train step incl. NCCL) replayed; --no-graphs = eager"}
 
@@ -457,7 +458,8 @@ def main():
     replica_div = None
     if distributed:   # codebook replicas must stay identical across ranks
         from vq_gnn_b200 import dist as vdist
-        replica_div = max(max(vdist.replicas_max_abs_diff(l.bank.E), vdist.replicas_max_abs_diff(l.bank.size))
+        replica_div = max(max(vdist.replicas_max_abs_diff(l.bank.E), vdist.replicas_max_abs_diff(l.bank.size),
+                              vdist.replicas_max_abs_diff(l.bank.codes.float()))
                           for l in model.convs)
 
     # ---- attribution pass: CUDA events around every C-ABI launch (dominant kernel + roofline) ---

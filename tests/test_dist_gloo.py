@@ -105,6 +105,20 @@ def _worker(rank, world_size, port, tmp):
                 assert torch.allclose(mine.dump()[k], v, rtol=1e-4, atol=1e-6), (step, k)
             for k, v in mine.dump().items():                              # replicas identical on every rank
                 assert vdist.replicas_max_abs_diff(v) == 0.0, (step, k)
+        # ---- code-table updates: every replica applies every rank's re-assignments, in rank order ------
+        Nn, nbr, Bc = 50, 3, 8
+        table = torch.zeros(Nn, nbr, dtype=torch.int16)
+        gg = torch.Generator().manual_seed(11)                           # same stream on both ranks
+        idx_all = [torch.randperm(Nn, generator=gg)[:Bc].to(torch.int32) for _ in range(world_size)]
+        idx_all[1][0] = idx_all[0][0]                                    # a node shared by two ranks' batches
+        new_all = [torch.randint(0, 99, (Bc, nbr), generator=gg, dtype=torch.int16) for _ in range(world_size)]
+        table[idx_all[rank].long()] = new_all[rank]                      # own update (what the assign kernel does)
+        gidx = vdist.allgather_code_updates_(table, idx_all[rank], new_all[rank])
+        want = torch.zeros(Nn, nbr, dtype=torch.int16)
+        for rr in range(world_size):
+            want[idx_all[rr].long()] = new_all[rr]
+        assert torch.equal(table, want) and gidx.numel() == world_size * Bc
+        assert vdist.replicas_max_abs_diff(table.float()) == 0.0
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:

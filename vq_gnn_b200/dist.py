@@ -67,6 +67,29 @@ def allreduce_mean_grads_(params: Iterable[Tensor], group=None) -> None:
         off += g.numel()
 
 
+def allgather_code_updates_(codes: Tensor, batch_idx: Tensor, new_codes: Tensor, k0: int = 0, group=None):
+    """Apply every OTHER rank's code-table updates to this rank's replica.
+
+    codes [N, nb] int16 is the local replica (already holding this rank's own update), batch_idx [B] the global
+    node ids this rank just re-assigned, new_codes [B, nbc] their codes for branches [k0, k0 + nbc).  Ranks are
+    applied in rank order, so when two ranks' batches share a node every replica ends with the same (highest
+    rank's) code.  Returns the gathered node ids [world * B] (for the group-major mirror), or None when single."""
+    rank, ws = world(group)
+    if ws == 1:
+        return None
+    B, nbc = new_codes.shape
+    gidx = torch.empty(ws * B, dtype=batch_idx.dtype, device=batch_idx.device)
+    gcodes = torch.empty(ws * B, nbc, dtype=new_codes.dtype, device=new_codes.device)
+    # codes travel as raw bytes: int16 is not a collective dtype on every backend
+    _timed("nccl_allgather_codes", lambda: (
+        dist.all_gather_into_tensor(gidx, batch_idx.contiguous(), group=group),
+        dist.all_gather_into_tensor(gcodes.view(torch.uint8), new_codes.contiguous().view(torch.uint8), group=group)))
+    for r in range(ws):      # rank order => identical result on every replica (own slice included on purpose)
+        sl = slice(r * B, (r + 1) * B)
+        codes[gidx[sl].long(), k0:k0 + nbc] = gcodes[sl]
+    return gidx
+
+
 def replicas_max_abs_diff(t: Tensor, group=None) -> float:
     """max |t_rank - t_rank0| over ranks (0.0 for identical replicas): a cheap divergence check."""
     if world(group)[1] == 1:

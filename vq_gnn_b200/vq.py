@@ -176,9 +176,16 @@ class VQBank:
                 1 if self.warm_up_flag else 0, self.eps, self.scale[0], self.scale[1], _lib.ptr(rm_f),
                 _lib.ptr(rv_f), _lib.ptr(rm_g) if joint else None, _lib.ptr(rv_g) if joint else None,
                 _lib.ptr(size), _lib.ptr(Wm), _lib.ptr(E), _lib.ptr(O), _lib.ptr(self.status), st))
+        touched, n_touched = bidx, B
+        if codes_ptr is not None and self.distributed:
+            # every replica of the code table learns the other ranks' re-assignments (their batch nodes are this
+            # rank's out-of-batch neighbours): one all-gather of (node id, codes) per update
+            gidx = dist.allgather_code_updates_(self.codes, bidx, idx, k0, self.process_group)
+            if gidx is not None:
+                touched, n_touched = gidx, int(gidx.numel())
         if codes_ptr is not None and self.codes_g is not None and not self._codes_g_dirty:
-            if k0 == 0 and nbc == self.nb:    # keep the group-major mirror in step (batch rows only)
-                _lib.check(lib.vqgnn_codes_group(_lib.ptr(self.codes), self.nb, _lib.ptr(bidx), B,
+            if k0 == 0 and nbc == self.nb:    # keep the group-major mirror in step (re-assigned rows only)
+                _lib.check(lib.vqgnn_codes_group(_lib.ptr(self.codes), self.nb, _lib.ptr(touched), n_touched,
                                                  self.codes.shape[0], self.G, _lib.ptr(self.codes_g), st))
             else:
                 self._codes_g_dirty = True
