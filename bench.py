@@ -362,14 +362,28 @@ def main():
 
     side = torch.cuda.Stream(device=dev)
 
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()     # double-buffered D2H target for the step results
+
     def e2e_run(n):
+        """Every step: H2D of the batch, plan build, train step, and a D2H copy of the step's loss.  The loss of
+        step i is copied asynchronously into pinned memory and READ on the host one step later (after its event),
+        so the host never idles the GPU waiting for the step it has just launched."""
         pf = DevicePrefetcher(host, dev, prepare=prep, count=n, stream=side)
-        last = 0.0
+        pending, last = None, 0.0
         for i in range(n):
             x, plan, y = pf.next()
             flush_l2()
             loss = train_step(model, opt_eager, x, plan, y, distributed)
-            last = float(loss.item())                                          # D2H read of the step's result
+            loss_host[i & 1].copy_(loss.detach(), non_blocking=True)           # D2H of this step's result
+            ev_l = torch.cuda.Event()
+            ev_l.record()
+            if pending is not None:
+                pending[0].synchronize()
+                last = float(loss_host[pending[1]])                             # host read of the previous step's loss
+            pending = (ev_l, i & 1)
+        if pending is not None:
+            pending[0].synchronize()
+            last = float(loss_host[pending[1]])
         pf.drain()
         return last
 
