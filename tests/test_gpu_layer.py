@@ -100,6 +100,7 @@ def test_literal_v2_hooks_never_fire():
     sd = {k: v.clone() for k, v in layer.state_dict().items()}
     o = restate.OracleLayer(C, 6, M, 4, N, "GCN", "v2", warm_up_flag=True, hook_mode="literal_v2").load_state_dict(sd)
     layer = layer.to(dev)
+    layer.materialize_tail = 'force'      # v2: dense rows of gathered codewords (no-op for v1 / GAT)
     x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
     _compare(_run_cuda(layer, batch_A, x, 3, dev), _run_oracle(o, batch_A, x, 3), layer, o)
     assert float(layer.bank.O[:, :, 4:].abs().sum()) == 0

@@ -88,6 +88,25 @@ __global__ void __launch_bounds__(kMpWarps * 32)
   if (info) info_reduce(static_cast<double>(fpart), ws_sum, ws_count, info_scale, info);
 }
 
+// tail_feat[t, :] / tail_grad[t, :] = feature / gradient codewords of tail entry t, all branches (D == 4, Wp == 8):
+// one warp per tail entry, one 256-bit codeword load per lane (= branch)
+__global__ void __launch_bounds__(256)
+    tail_materialize_kernel(const int32_t* __restrict__ tail_node, int64_t T, const int16_t* __restrict__ codes,
+                            const float* __restrict__ O, int nb, int M, float* __restrict__ xt, int64_t ldx,
+                            float* __restrict__ gt, int64_t ldg) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (t >= T) return;
+  const int64_t node = tail_node ? __ldg(tail_node + t) : t;
+  for (int k = lane; k < nb; k += 32) {
+    const int code = __ldg(codes + node * nb + k);
+    float f[4], g[4];
+    ld_sector(O + (static_cast<int64_t>(k) * M + code) * 8, f, g);
+    if (xt) st_vec<4>(xt + t * ldx + 4 * k, f);
+    if (gt) st_vec<4>(gt + t * ldg + 4 * k, g);
+  }
+}
+
 // dx <- gq_scale * dinfo * gq  (or 0): the part of the backward that does not depend on the CSR
 template <int VEC>
 __global__ void mp_bwd_init_kernel(int64_t B, int C, const float* __restrict__ gq, int64_t ldgq, float gq_scale,
@@ -161,10 +180,25 @@ extern "C" int vqgnn_mp_chunk_rows(const int32_t* rowptr, int64_t R, int64_t nnz
   return VQGNN_OK;
 }
 
+extern "C" int vqgnn_tail_materialize(const int32_t* tail_node, int64_t T, const int16_t* codes, const float* O,
+                                      int nb, int M, int D, int Wp, float* tail_feat, float* tail_grad,
+                                      int64_t ld_tail, void* stream) {
+  VQ_CHECK_ARG(codes && O && T >= 0 && nb > 0 && (tail_feat || tail_grad), "tail_materialize: bad arguments");
+  VQ_CHECK_ARG(D == 4 && Wp == 8 && aligned32(O) && ld_tail % 4 == 0 && ld_tail >= 4 * nb &&
+                   (!tail_feat || aligned16(tail_feat)) && (!tail_grad || aligned16(tail_grad)),
+               "tail_materialize: needs D == 4, Wp == 8 and 16 B aligned outputs");
+  if (T == 0) return VQGNN_OK;
+  tail_materialize_kernel<<<ceil_div(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      tail_node, T, codes, O, nb, M, tail_feat, ld_tail, tail_grad, ld_tail);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}
+
 extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
                             const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
                             const float* x, int64_t ldx, const int32_t* tail_node, const int16_t* codes,
-                            const float* O, int nb, int M, int D, int Wp, float feat_scale, float info_scale,
+                            const float* O, int nb, int M, int D, int Wp, const float* tail_feat,
+                            int64_t ld_tail, float feat_scale, float info_scale,
                             float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws,
                             void* stream) {
   VQ_CHECK_ARG(rowptr && col && val && x && codes && O && y, "mp_fwd: null argument");
@@ -175,6 +209,10 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C = nb * D;
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
+  if (tail_feat) {
+    VQ_CHECK_ARG(!rval && ld_tail % 4 == 0 && aligned16(tail_feat), "mp_fwd: dense tail rows need rval == NULL and 16 B alignment");
+    cb.tail_feat = tail_feat, cb.ld_tail = ld_tail;
+  }
   double* ws_sum = static_cast<double*>(ws);
   unsigned int* ws_count = ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 8) : nullptr;
   if (info) VQ_CUDA(cudaMemsetAsync(ws, 0, 16, s));
@@ -215,8 +253,9 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
 extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
                             const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* dy,
                             int64_t lddy, const int32_t* tail_node, const int16_t* codes, const float* O, int nb,
-                            int M, int D, int Wp, float tail_scale, const float* gq, int64_t ldgq,
-                            float gq_scale, const float* dinfo, float* dx, int64_t lddx, void* stream) {
+                            int M, int D, int Wp, const float* tail_grad, int64_t ld_tail, float tail_scale,
+                            const float* gq, int64_t ldgq, float gq_scale, const float* dinfo, float* dx,
+                            int64_t lddx, void* stream) {
   VQ_CHECK_ARG(browptr && brow && bval && dy && codes && O && dx, "mp_bwd: null argument");
   VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && nb > 0 && D > 0 && Wp >= 2 * D, "mp_bwd: bad sizes");
   VQ_CHECK_ARG(nnz >= 0 && nnz < (1ll << 31), "mp_bwd: nnz must fit int32");
@@ -224,6 +263,10 @@ extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const f
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C = nb * D;
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
+  if (tail_grad) {
+    VQ_CHECK_ARG(ld_tail % 4 == 0 && aligned16(tail_grad), "mp_bwd: dense tail rows must be 16 B aligned");
+    cb.tail_grad = tail_grad, cb.ld_tail = ld_tail;
+  }
   const bool vec4 = (D == 4) && (Wp % 4 == 0) && (lddy % 4 == 0) && (lddx % 4 == 0) && aligned16(dy) &&
                     aligned16(dx) && aligned16(O) && (!gq || (ldgq % 4 == 0 && aligned16(gq)));
   const int vec = vec4 ? 4 : 1;

@@ -16,6 +16,12 @@ struct Codebook {
   const int16_t* codes;      // [N, nb]
   const float* O;            // [nb, M, Wp]
   int nb, M, D, Wp;
+  // optional dense copies of the tail entries' codewords (vqgnn_tail_materialize): row t = tail entry t.  When a
+  // tail node is referenced by many edges (v2 batch graphs: ~20x), gathering its codewords ONCE and reading a
+  // coalesced dense row per edge replaces nb scattered 32 B sectors per edge by C*4 contiguous bytes.
+  const float* tail_feat = nullptr;  // [T, ld_tail] feature halves
+  const float* tail_grad = nullptr;  // [T, ld_tail] gradient halves
+  int64_t ld_tail = 0;
 };
 
 template <int VEC>
@@ -155,6 +161,24 @@ __device__ __forceinline__ void gather_accumulate(const EntryGroup& g, int B, co
                                                   int c0, int k, int off, float (&acc)[VEC], float (&gqa)[VEC]) {
   constexpr int U = kMpUnroll;
   const float* p[U];
+  const float* tdense = half_off == 0 ? cb.tail_feat : cb.tail_grad;  // uniform: dense tail rows available?
+  if (!WIDE && !HAS_GQ && tdense != nullptr) {
+    float a[U][VEC];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (g.c[u] >= B) ld_vec<VEC>(tdense + static_cast<int64_t>(g.c[u] - B) * cb.ld_tail + c0, a[u]);
+      else if (g.c[u] >= 0) ld_vec<VEC>(dense + static_cast<int64_t>(g.c[u]) * ldd + c0, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (g.c[u] >= 0) {
+        const float s = g.c[u] >= B ? g.v[u] * tscale : g.v[u];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(s, a[u][i], acc[i]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < U; ++u) {  // first level: code loads for tail entries (independent)
     p[u] = nullptr;
