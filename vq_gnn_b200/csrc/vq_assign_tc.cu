@@ -36,7 +36,7 @@ constexpr int kBTileBytes = kTileN * kK * 4;   // 32 KB
 constexpr int kALbo = (kTileM / 8) * 128;      // bytes between the two 16 B K-chunks of one MMA (A)
 constexpr int kBLbo = (kTileN / 8) * 128;      // same for B
 constexpr int kSbo = 128;                      // bytes between 8-row core matrices
-constexpr size_t kSmemBytes = 1024 + kATileBytes + kStages * kBTileBytes + 4096;  // > 113.5 KB: one CTA per SM
+constexpr size_t kSmemBytes = 1024 + 2 * kATileBytes + kStages * kBTileBytes + 4096;  // 165 KB: one CTA per SM
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -152,7 +152,7 @@ __global__ void pack_codebook_kernel(const float* __restrict__ E, int nb, int M,
 // ------------------------------------------------------------------------------------------------
 // the assignment kernel
 // ------------------------------------------------------------------------------------------------
-template <int W>  // packed width D + Dg used by this launch (4: feature only, 8: joint, 9: joint + add_flag)
+template <int W, bool VLD>  // W: packed width D + Dg (4: feature only, 8: joint, 9: joint + add_flag); VLD: 128-bit row loads
 __global__ void __launch_bounds__(kThreads, 1)
     vq_assign_tc_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g, int64_t ldg,
                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   static_assert(3 * W + 2 <= kK, "packed contraction does not fit");
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* a_tile = smem;
-  unsigned char* b_tiles = smem + kATileBytes;
+  unsigned char* a_tile = smem;                         // two A' buffers: item i+1 is staged while item i drains
+  unsigned char* b_tiles = smem + 2 * kATileBytes;
   unsigned char* misc = b_tiles + kStages * kBTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc);  // [0..2] b_full, [3..5] b_empty, [6..7] acc_full, [8..9] acc_empty, [10] a_ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 128);
@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int B_FULL = 0, B_EMPTY = kStages, ACC_FULL = 2 * kStages, ACC_EMPTY = 2 * kStages + 2,
-                A_READY = 2 * kStages + 4;
+                A_READY = 2 * kStages + 4;  // two barriers, one per A' buffer
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(BAR(B_FULL + s), 1), mbar_init(BAR(B_EMPTY + s), 1);
     for (int b = 0; b < 2; ++b) mbar_init(BAR(ACC_FULL + b), 1), mbar_init(BAR(ACC_EMPTY + b), kEpiThreads);
-    mbar_init(BAR(A_READY), 1);
+    mbar_init(BAR(A_READY), 1), mbar_init(BAR(A_READY + 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kEpiWarps + 1) {  // TMEM: all 512 columns (two 128 x 256 fp32 accumulators)
@@ -230,9 +230,10 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t gt = 0, it = 0;
-      const uint32_t a_addr = smem_u32(a_tile);
+      const uint32_t a_addr0 = smem_u32(a_tile);
       for (int64_t item = item_begin; item < item_end; ++item, ++it) {
-        mbar_wait(BAR(A_READY), it & 1);
+        const uint32_t a_addr = a_addr0 + (it & 1) * kATileBytes;
+        mbar_wait(BAR(A_READY + (it & 1)), (it >> 1) & 1);
         for (int j = 0; j < tiles_per_item; ++j, ++gt) {
           const int s = resident ? j : gt % kStages, buf = gt & 1;
           const uint32_t use = resident ? it : gt / kStages;
@@ -256,42 +257,74 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q = warp & 3, h = warp >> 2;  // TMEM lane quarter, column quarter (64 of the tile's 256)
     const int rl = 32 * q + lane;  // row inside the tile == TMEM lane
     uint32_t gt = 0;
-    for (int64_t item = item_begin; item < item_end; ++item) {
+    // RAW row of an item for this thread's row (zeros past B / past the last item).  Nothing here may depend on the
+    // loaded values: the loads are issued two items ahead and must stay in flight (an ncu source view of the first
+    // pipelined version showed 40 % of the stall samples on the whitening FFMAs that consumed them immediately).
+    auto load_raw = [&](int64_t item, float (&z)[W]) {
       const int k = static_cast<int>(item / row_tiles);
       const int64_t b = (item - static_cast<int64_t>(k) * row_tiles) * kTileM + rl;
-      // ---- whiten the row, split into TF32 hi/lo, write this thread's half of the A' row ----
-      float z[W];
-      float a[kK];
 #pragma unroll
-      for (int j = 0; j < kK; ++j) a[j] = 0.f;
+      for (int w = 0; w < W; ++w) z[w] = 0.f;
+      if (item >= item_end || b >= B || h != 0) return;   // the h == 0 warps own their rows: load, whiten, stage, emit
+      if constexpr (VLD) {   // D == 4, 16 B aligned rows: one 128-bit load per operand instead of four scalar ones
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * ldx + k * 4));
+        z[0] = xv.x, z[1] = xv.y, z[2] = xv.z, z[3] = xv.w;
+        if constexpr (W == 8) {
+          const float4 gv = __ldg(reinterpret_cast<const float4*>(g + b * ldg + k * 4));
+          z[4] = gv.x, z[5] = gv.y, z[6] = gv.z, z[7] = gv.w;
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          z[w] = (w < D) ? __ldg(x + b * ldx + k * D + w) : __ldg(g + b * ldg + k * Dg + (w - D));
+      }
+    };
+    // z = raw * scale + shift of the item's branch (vq.py:223-227 folded into one affine per column)
+    auto whiten = [&](int64_t item, float (&z)[W]) {
+      const int k = static_cast<int>(item / row_tiles);
+      const int64_t b = (item - static_cast<int64_t>(k) * row_tiles) * kTileM + rl;
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        float v = 0.f;
-        if (b < B) {
-          if (w < D) {
-            const int c = k * D + w;
-            v = fmaf(__ldg(x + b * ldx + c), __ldg(scale + c), __ldg(shift + c));
-          } else {
-            const int cg = k * Dg + (w - D);
-            v = fmaf(__ldg(g + b * ldg + cg), __ldg(scale + C + cg), __ldg(shift + C + cg));
-          }
-        }
-        z[w] = v;
-        const float hi = to_tf32(v), lo = to_tf32(v - hi);
-        a[w] = hi, a[W + w] = lo, a[2 * W + w] = hi;
+        const int c = (w < D) ? k * D + w : C + k * Dg + (w - D);
+        z[w] = (item < item_end && b < B) ? fmaf(z[w], __ldg(scale + c), __ldg(shift + c)) : 0.f;
       }
-      a[3 * W] = 1.f, a[3 * W + 1] = 1.f;
-      {
-        unsigned char* dst = a_tile + (rl >> 3) * 128 + (rl & 7) * 16;
+    };
+    // split into TF32 hi/lo, write this thread's quarter of the A' row into buffer (it & 1), publish it
+    auto stage_a = [&](uint32_t it, const float (&z)[W]) {
+      if (h == 0) {   // one thread per row writes the whole 128 B A' row (8 K chunks of 16 B)
+        float a[kK];
 #pragma unroll
-        for (int kk = 0; kk < kK / 4; ++kk) {  // this thread's quarter of the K chunks (compile-time register indices)
-          if ((kk >> 1) == h)
-            *reinterpret_cast<float4*>(dst + kk * kALbo) = make_float4(a[4 * kk], a[4 * kk + 1], a[4 * kk + 2], a[4 * kk + 3]);
+        for (int j = 0; j < kK; ++j) a[j] = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const float hi = to_tf32(z[w]), lo = to_tf32(z[w] - hi);
+          a[w] = hi, a[W + w] = lo, a[2 * W + w] = hi;
         }
+        a[3 * W] = 1.f, a[3 * W + 1] = 1.f;
+        unsigned char* dst = a_tile + (it & 1) * kATileBytes + (rl >> 3) * 128 + (rl & 7) * 16;
+#pragma unroll
+        for (int kk = 0; kk < kK / 4; ++kk)
+          *reinterpret_cast<float4*>(dst + kk * kALbo) = make_float4(a[4 * kk], a[4 * kk + 1], a[4 * kk + 2], a[4 * kk + 3]);
+        fence_async_smem();
       }
-      fence_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      if (threadIdx.x == 0) mbar_arrive(BAR(A_READY));
+      if (threadIdx.x == 0) mbar_arrive(BAR(A_READY + (it & 1)));
+    };
+    // software pipeline over items: rows are loaded two items ahead, the A' tile is staged one item ahead (its
+    // buffer was last read by the MMAs of item it-1, which this thread has already drained), so the MMAs of item
+    // it+1 run while item it's accumulators are being read out of TMEM
+    float z[W], z1[W], z2[W];   // z: whitened row of the current item; z1 / z2: raw rows of the next two
+    load_raw(item_begin, z);
+    load_raw(item_begin + 1, z1);
+    whiten(item_begin, z);
+    if (item_begin < item_end) stage_a(0, z);
+    uint32_t it = 0;
+    for (int64_t item = item_begin; item < item_end; ++item, ++it) {
+      const int k = static_cast<int>(item / row_tiles);
+      const int64_t b = (item - static_cast<int64_t>(k) * row_tiles) * kTileM + rl;
+      load_raw(item + 2, z2);
+      whiten(item + 1, z1);          // its loads were issued one whole item ago
+      if (item + 1 < item_end) stage_a(it + 1, z1);
 
       // ---- scan the accumulator tiles ----
       float best = __int_as_float(0x7f800000);
@@ -348,6 +381,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           atomicAdd(dst + Wp, 1.0f);
         }
       }
+#pragma unroll
+      for (int w = 0; w < W; ++w) z[w] = z1[w], z1[w] = z2[w];
     }
   }
 
@@ -382,16 +417,24 @@ int launch_assign_tc(const float* x, int64_t ldx, const float* g, int64_t ldg, c
   VQ_LAUNCH_CHECK();
   const int64_t n_items = static_cast<int64_t>(nb) * ((B + kTileM - 1) / kTileM);
   const int grid = static_cast<int>(std::min<int64_t>(n_items, kNumSMs));
-#define VQ_TC_LAUNCH(WW)                                                                                   \
+  const bool vld = (D == 4) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   (!g || (Dg == 4 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0));
+#define VQ_TC_LAUNCH(WW, VV)                                                                               \
   do {                                                                                                     \
-    auto kern = vq_assign_tc_kernel<WW>;                                                                   \
+    auto kern = vq_assign_tc_kernel<WW, VV>;                                                                \
     VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));     \
     kern<<<grid, kThreads, kSmemBytes, s>>>(x, ldx, g, ldg, scale, shift, Bp, B, nb, M, M_pad, D, Dg, Wp,  \
                                             batch_idx, codes, codes_ld, idx, stats);                       \
   } while (0)
-  if (W == 4) VQ_TC_LAUNCH(4);
-  else if (W == 8) VQ_TC_LAUNCH(8);
-  else VQ_TC_LAUNCH(9);
+  if (W == 4) {
+    if (vld) VQ_TC_LAUNCH(4, true);
+    else VQ_TC_LAUNCH(4, false);
+  } else if (W == 8) {
+    if (vld) VQ_TC_LAUNCH(8, true);
+    else VQ_TC_LAUNCH(8, false);
+  } else {
+    VQ_TC_LAUNCH(9, false);
+  }
 #undef VQ_TC_LAUNCH
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
