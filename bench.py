@@ -129,7 +129,7 @@ def build_workload(dev, rank: int, world: int, scale: float = 1.0, n_batches: in
     return g, batches
 
 
-def build_model(dev, N, distributed: bool, assign_impl: int = 0):
+def build_model(dev, N, distributed: bool, assign_impl='auto'):
     import vq_gnn_b200 as V
     c = CFG
     torch.manual_seed(0)
@@ -138,7 +138,7 @@ def build_model(dev, N, distributed: bool, assign_impl: int = 0):
                          bn_flag=True, warm_up_flag=True, momentum=0.1, conv_type=c["conv"], version=c["version"])
     model = model.to(dev).train()
     for layer in model.convs:
-        layer.bank.assign_impl = assign_impl
+        layer.bank.assign_impl = assign_impl if assign_impl == 'auto' else int(assign_impl)
         layer.bank.distributed = distributed
     return model
 
@@ -245,8 +245,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the synthetic graph (debug only)")
-    ap.add_argument("--assign-impl", type=int, default=int(os.environ.get("VQGNN_ASSIGN_IMPL", "1")),
-                    help="1 = tcgen05/TMEM assignment kernel (default), 0 = exact-fp32 SIMT kernel")
+    ap.add_argument("--assign-impl", type=str, default=os.environ.get("VQGNN_ASSIGN_IMPL", "auto"),
+                    help="auto (default: tcgen05/TMEM kernel when M >= 512), 1 = always tcgen05, 0 = exact-fp32 SIMT")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true",
                     help="launch the device-resident steps eagerly instead of replaying one CUDA graph per batch")
@@ -545,7 +545,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "nodes/s/layer", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "replica_max_abs_diff": replica_div, "cuda_graphs": graphs is not None, "kernels": kernel_table, "assign_impl": "tcgen05" if args.assign_impl == 1 else "simt-fp32"}
+                "replica_max_abs_diff": replica_div, "cuda_graphs": graphs is not None, "kernels": kernel_table, "assign_impl": {"auto": "tcgen05 (auto: M=1024)", "1": "tcgen05", "0": "simt-fp32"}[str(args.assign_impl)]}
         print(json.dumps(line), flush=True)
     if distributed:
         torch.distributed.barrier()

@@ -215,18 +215,21 @@ int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, cons
 /* a_l[n] = <Xin[n], att_l>, a_r[n] = <Xin[n], att_r> for n < R (convs.py:188-190);
  * stat[0] = max_n a_l[n], stat[1] = max_n a_r[n] ("Trick 1" scale, convs.py:209-211). */
 int vqgnn_gat_scores(int64_t R, int64_t B, const float* x, int64_t ldx, const int32_t* tail_node,
-                     const int16_t* codes, const float* O, int nb, int M, int D, int Wp, const float* att_l,
-                     const float* att_r, float* a_l, float* a_r, float* stat, void* stream);
+                     const int16_t* codes, const float* O, int nb, int M, int D, int Wp, const float* tail_feat,
+                     int64_t ld_tail, const float* att_l, const float* att_r, float* a_l, float* a_r,
+                     float* stat, void* stream);
 
 /* sigma = sqrt(stat[0]^2+1) sqrt(stat[1]^2+1); w_ij = val * exp(leaky_relu((a_l[j]+a_r[i])/sigma, slope));
  * rows i < B:  den[i] = sum_j w_ij ; y[i, :C] = sum_j w_ij Xin[j, :C] / (den[i] + 1e-16)
  * rows i >= B: info += <sum_j w_ij Xin[j, :C], O_k[code(node(i-B)), D:2D]>   (un-normalised, models.py:198)
- * *info = info_scale * info.  Partition arguments as in vqgnn_mp_fwd. */
+ * *info = info_scale * info.  Partition arguments as in vqgnn_mp_fwd.  tail_feat / tail_grad (here and in the
+ * other two entry points): optional dense rows from vqgnn_tail_materialize, NULL = gather per use. */
 int vqgnn_gat_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* chunk_row,
                   int chunk, int64_t nnz, int64_t R, int64_t B, const float* x, int64_t ldx,
                   const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M, int D, int Wp,
-                  const float* a_l, const float* a_r, const float* stat, float negative_slope,
-                  float info_scale, float* y, int64_t ldy, float* den, float* info, void* ws, void* stream);
+                  const float* tail_feat, int64_t ld_tail, const float* a_l, const float* a_r, const float* stat,
+                  float negative_slope, float info_scale, float* y, int64_t ldy, float* den, float* info,
+                  void* ws, void* stream);
 
 /* Backward of vqgnn_gat_scores + vqgnn_gat_fwd given dout = d loss / d y [B, C] and dinfo (device scalar or
  * NULL = 1); `out` is the forward's y.  Outputs:
@@ -239,6 +242,7 @@ int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const float* val, c
                   int64_t nnz, int64_t R, const int32_t* browptr, const int32_t* brow, const float* bval,
                   const int32_t* bchunk_row, int64_t bnnz, int chunk, int64_t B, const float* x, int64_t ldx,
                   const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M, int D, int Wp,
+                  const float* tail_feat, const float* tail_grad, int64_t ld_tail,
                   const float* att_l, const float* att_r, const float* a_l, const float* a_r, const float* stat,
                   float negative_slope, const float* out, int64_t ldo, const float* den, const float* dout,
                   int64_t lddo, float tail_scale, const float* dinfo, float* dyn, int64_t lddyn, float* dden,

@@ -3,7 +3,7 @@ import torch, bench
 from vq_gnn_b200.loader import DevicePrefetcher
 dev = torch.device("cuda:0")
 g, batches = bench.build_workload(dev, 0, 1, 1.0, n_batches=4)
-model = bench.build_model(dev, g.N, False, 1)
+model = bench.build_model(dev, g.N, False, 'auto')
 opt = torch.optim.RMSprop(model.parameters(), lr=1e-3, alpha=0.99)
 bench.warm_start(model, batches)
 host = []

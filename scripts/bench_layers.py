@@ -80,7 +80,8 @@ def main():
         torch.manual_seed(0)
         layer = V.LowRankGNNLayer(*H.layer_args(C, C, s["M"], 4, s["N"], s["conv"], skip=False),
                                   version=s["version"]).to(dev).train()
-        layer.bank.assign_impl = int(os.environ.get("VQGNN_ASSIGN_IMPL", "1"))
+        impl = os.environ.get("VQGNN_ASSIGN_IMPL", "auto")
+        layer.bank.assign_impl = impl if impl == "auto" else int(impl)
         plan = V.build_plan(bA, s["conv"], s["N"], True, dev).warm()
         x = torch.randn(B, C, device=dev)
         w = torch.randn(B, C, device=dev)

@@ -48,12 +48,13 @@ _SIGNATURES = {
     "vqgnn_plan_v1_workspace_bytes": (C.c_size_t, [i64, i64]),
     "vqgnn_plan_v1_build": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "vqgnn_gat_scores": (C.c_int, [i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "vqgnn_gat_scores": (C.c_int, [i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp, vp,
+                                   vp]),
     "vqgnn_gat_fwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32,
-                                vp, vp, vp, f32, f32, vp, i64, vp, vp, vp, vp]),
+                                vp, i64, vp, vp, vp, f32, f32, vp, i64, vp, vp, vp, vp]),
     "vqgnn_gat_bwd": (C.c_int, [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, i64, i32, i64, vp, i64, vp, vp, vp,
-                                i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp, i64, vp, vp, i64, f32, vp,
-                                vp, i64, vp, vp, vp, vp, i64, vp, vp, vp]),
+                                i32, i32, i32, i32, vp, vp, i64, vp, vp, vp, vp, vp, f32, vp, i64, vp, vp, i64,
+                                f32, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp]),
     "vqgnn_gat1_scores": (C.c_int, [i64, vp, i64, vp, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "vqgnn_gat1_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i64, vp, i64, vp, vp, i32, i32, i32, i32, f32,
                                  vp, vp, vp, vp, f32, vp, i64, vp, vp, vp, vp]),

@@ -50,6 +50,8 @@ __device__ __forceinline__ void load_xin(int n, int B, const float* __restrict__
                                          const Codebook& cb, int c0, int k, int off, float (&v)[VEC]) {
   if (n < B) {
     ld_vec<VEC>(x + static_cast<int64_t>(n) * ldx + c0, v);
+  } else if (cb.tail_feat) {   // dense rows of gathered codewords (vqgnn_tail_materialize)
+    ld_vec<VEC>(cb.tail_feat + static_cast<int64_t>(n - B) * cb.ld_tail + c0, v);
   } else {
     const int node = cb.tail_node ? __ldg(cb.tail_node + (n - B)) : (n - B);
     const int code = __ldg(cb.codes + static_cast<int64_t>(node) * cb.nb + k);
@@ -115,6 +117,9 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     auto body = [&](const EntryGroup& g) {
       if (t.active) gather_accumulate<VEC, false, false>(g, B, x, ldx, cb, 0, 1.f, t.c0, t.k, t.off, acc, unused);
     };
+    auto body_dense = [&](const EntryGroup& g) {
+      if (t.active) gather_accumulate<VEC, false, false, true>(g, B, x, ldx, cb, 0, 1.f, t.c0, t.k, t.off, acc, unused);
+    };
     auto flush = [&](int r, bool whole) {
       if (t.active) {
         if (r < B) {
@@ -139,7 +144,10 @@ __global__ void __launch_bounds__(kMpWarps * 32)
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
       pol.den = 0.f;
     };
-    walk_rows<false>(t.eb, t.ee, t.row0, R, rowptr, col, val, nullptr, B, cb.tail_node, lane, pol, body, flush);
+    if (cb.tail_feat != nullptr)
+      walk_rows<false>(t.eb, t.ee, t.row0, R, rowptr, col, val, nullptr, B, cb.tail_node, lane, pol, body_dense, flush);
+    else
+      walk_rows<false>(t.eb, t.ee, t.row0, R, rowptr, col, val, nullptr, B, cb.tail_node, lane, pol, body, flush);
   }
   if (info) info_reduce(static_cast<double>(fpart), ws_sum, ws_count, info_scale, info);
 }
@@ -216,9 +224,13 @@ __global__ void __launch_bounds__(kMpWarps * 32)
         ld_vec<VEC>(dyn + static_cast<int64_t>(r) * lddyn + c0, dy);
         if (ones) dd = __ldg(dden + r);
       } else {
-        const int node = cb->tail_node ? __ldg(cb->tail_node + (r - B)) : (r - B);
-        const int code = __ldg(cb->codes + static_cast<int64_t>(node) * cb->nb + k);
-        ld_vec<VEC>(cb->O + (static_cast<int64_t>(k) * cb->M + code) * cb->Wp + cb->D + off, dy);
+        if (cb->tail_grad) {
+          ld_vec<VEC>(cb->tail_grad + static_cast<int64_t>(r - B) * cb->ld_tail + c0, dy);
+        } else {
+          const int node = cb->tail_node ? __ldg(cb->tail_node + (r - B)) : (r - B);
+          const int code = __ldg(cb->codes + static_cast<int64_t>(node) * cb->nb + k);
+          ld_vec<VEC>(cb->O + (static_cast<int64_t>(k) * cb->M + code) * cb->Wp + cb->D + off, dy);
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) dy[i] *= ts;
       }
@@ -284,13 +296,20 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     if (t.active)
       gather_accumulate<VEC, false, false>(g, B, dyn, lddyn, cb, cb.D, ts, t.c0, t.k, t.off, acc, unused);
   };
+  auto body_dense = [&](const EntryGroup& g) {
+    if (t.active)
+      gather_accumulate<VEC, false, false, true>(g, B, dyn, lddyn, cb, cb.D, ts, t.c0, t.k, t.off, acc, unused);
+  };
   auto flush = [&](int j, bool) {
     if (t.active) red_vec<VEC>(dx + static_cast<int64_t>(j) * lddx + t.c0, acc);  // dx is pre-zeroed
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
     pol.den = 0.f;
   };
-  walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body, flush);
+  if (cb.tail_grad != nullptr)
+    walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body_dense, flush);
+  else
+    walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body, flush);
 }
 
 // (B3) ds -> da through a = s * sigma, sigma = sqrt(max(a_l)^2+1) sqrt(max(a_r)^2+1).  One CTA.
@@ -426,14 +445,24 @@ static GatShape gat_shape(int nb, int D, int Wp, const void* O, std::initializer
 
 using namespace vqgnn;
 
+// dense tail rows (vqgnn_tail_materialize) are optional everywhere below: NULL = gather codewords per use
+static int gat_set_tail(Codebook& cb, const float* tail_feat, const float* tail_grad, int64_t ld_tail) {
+  VQ_CHECK_ARG((!tail_feat && !tail_grad) || (ld_tail % 4 == 0 && (!tail_feat || aligned16(tail_feat)) &&
+                                               (!tail_grad || aligned16(tail_grad))),
+               "gat: dense tail rows must be 16 B aligned");
+  cb.tail_feat = tail_feat, cb.tail_grad = tail_grad, cb.ld_tail = ld_tail;
+  return VQGNN_OK;
+}
+
 extern "C" int vqgnn_gat_scores(int64_t R, int64_t B, const float* x, int64_t ldx, const int32_t* tail_node,
                                 const int16_t* codes, const float* O, int nb, int M, int D, int Wp,
-                                const float* att_l, const float* att_r, float* a_l, float* a_r, float* stat,
-                                void* stream) {
+                                const float* tail_feat, int64_t ld_tail, const float* att_l, const float* att_r,
+                                float* a_l, float* a_r, float* stat, void* stream) {
   VQ_CHECK_ARG(x && codes && O && att_l && att_r && a_l && a_r && stat, "gat_scores: null argument");
   VQ_CHECK_ARG(R >= B && B > 0 && R < (1ll << 31) && nb > 0 && D > 0 && Wp >= 2 * D, "gat_scores: bad sizes");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
+  if (int rc = gat_set_tail(cb, tail_feat, nullptr, ld_tail)) return rc;
   // att vectors hold C+1 floats: rows of the parameter are not 16 B aligned in general -> scalar loads there
   const GatShape g = gat_shape(nb, D, Wp, O, {x, att_l, att_r}, {ldx});
   gat_stat_init_kernel<<<1, 32, 0, s>>>(stat);
@@ -448,9 +477,10 @@ extern "C" int vqgnn_gat_scores(int64_t R, int64_t B, const float* x, int64_t ld
 extern "C" int vqgnn_gat_fwd(const int32_t* rowptr, const int32_t* col, const float* val,
                              const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
                              const float* x, int64_t ldx, const int32_t* tail_node, const int16_t* codes,
-                             const float* O, int nb, int M, int D, int Wp, const float* a_l, const float* a_r,
-                             const float* stat, float negative_slope, float info_scale, float* y, int64_t ldy,
-                             float* den, float* info, void* ws, void* stream) {
+                             const float* O, int nb, int M, int D, int Wp, const float* tail_feat, int64_t ld_tail,
+                             const float* a_l, const float* a_r, const float* stat, float negative_slope,
+                             float info_scale, float* y, int64_t ldy, float* den, float* info, void* ws,
+                             void* stream) {
   VQ_CHECK_ARG(rowptr && col && val && x && codes && O && a_l && a_r && stat && y && den, "gat_fwd: null argument");
   VQ_CHECK_ARG(R >= B && B > 0 && nb > 0 && D > 0 && Wp >= 2 * D, "gat_fwd: bad sizes");
   VQ_CHECK_ARG(!info || ws, "gat_fwd: info needs a workspace");
@@ -458,6 +488,7 @@ extern "C" int vqgnn_gat_fwd(const int32_t* rowptr, const int32_t* col, const fl
   VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "gat_fwd: needs chunk_row");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
+  if (int rc = gat_set_tail(cb, tail_feat, nullptr, ld_tail)) return rc;
   const GatShape g = gat_shape(nb, D, Wp, O, {x, y}, {ldx, ldy});
   double* ws_sum = static_cast<double*>(ws);
   unsigned int* ws_count = ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 8) : nullptr;
@@ -490,6 +521,7 @@ extern "C" int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const fl
                              const int32_t* brow, const float* bval, const int32_t* bchunk_row, int64_t bnnz,
                              int chunk, int64_t B, const float* x, int64_t ldx, const int32_t* tail_node,
                              const int16_t* codes, const float* O, int nb, int M, int D, int Wp,
+                             const float* tail_feat, const float* tail_grad, int64_t ld_tail,
                              const float* att_l, const float* att_r, const float* a_l, const float* a_r,
                              const float* stat, float negative_slope, const float* out, int64_t ldo,
                              const float* den, const float* dout, int64_t lddo, float tail_scale,
@@ -505,6 +537,7 @@ extern "C" int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const fl
                "gat_bwd: needs chunk rows");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
+  if (int rc = gat_set_tail(cb, tail_feat, tail_grad, ld_tail)) return rc;
   const GatShape g = gat_shape(nb, D, Wp, O, {x, dyn, dx, att_l, att_r}, {ldx, lddyn, dx ? lddx : 0});
   VQ_CHECK_ARG(g.nslab <= 8, "gat_bwd: at most %d columns are supported", 8 * 32 * g.vec);
   const int C = g.C;

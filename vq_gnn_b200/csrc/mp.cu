@@ -51,6 +51,12 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     auto body = [&](const EntryGroup& g) {
       if (t.active) gather_accumulate<VEC, HAS_GQ, WIDE>(g, B, x, ldx, cb, 0, feat_scale, c0, k, off, acc, gqa);
     };
+    auto body_dense = [&](const EntryGroup& g) {
+      if constexpr (!HAS_GQ && !WIDE) {
+        if (t.active)
+          gather_accumulate<VEC, false, false, true>(g, B, x, ldx, cb, 0, feat_scale, c0, k, off, acc, gqa);
+      }
+    };
     auto flush = [&](int r, bool whole) {
       if (t.active) {
         if (r < B) {
@@ -83,7 +89,10 @@ __global__ void __launch_bounds__(kMpWarps * 32)
       for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
     };
     PlainWeights pol;
-    walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body, flush);
+    if (!HAS_GQ && !WIDE && cb.tail_feat != nullptr)   // uniform over the grid
+      walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body_dense, flush);
+    else
+      walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body, flush);
   }
   if (info) info_reduce(static_cast<double>(fpart), ws_sum, ws_count, info_scale, info);
 }
@@ -148,13 +157,20 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     if (t.active)
       gather_accumulate<VEC, false, false>(g, B, dy, lddy, cb, cb.D, ts, t.c0, t.k, t.off, acc, unused);
   };
+  auto body_dense = [&](const EntryGroup& g) {
+    if (t.active)
+      gather_accumulate<VEC, false, false, true>(g, B, dy, lddy, cb, cb.D, ts, t.c0, t.k, t.off, acc, unused);
+  };
   auto flush = [&](int j, bool) {
     if (t.active) red_vec<VEC>(dx + static_cast<int64_t>(j) * lddx + t.c0, acc);  // onto the initialised dx
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
   };
   PlainWeights pol;
-  walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body, flush);
+  if (cb.tail_grad != nullptr)
+    walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body_dense, flush);
+  else
+    walk_rows<false>(t.eb, t.ee, t.row0, B, browptr, brow, bval, nullptr, B, cb.tail_node, lane, pol, body, flush);
 }
 
 }  // namespace vqgnn

@@ -155,14 +155,16 @@ __device__ __forceinline__ void walk_rows(int eb, int ee, int r, int64_t R, cons
 //   acc += v * (c < B ? dense[c, c0..] : tscale * O_k[code, half_off + off ..])
 //   gqa += rv * O_k[code, D + off ..]                                   (HAS_GQ, tail entries only)
 // WIDE: VEC == 4, HAS_GQ, Wp == 8, D == 4, half_off == 0 -> one 256-bit load per gathered codeword.
-template <int VEC, bool HAS_GQ, bool WIDE>
+// DENSE_TAIL: tail entries read row (c - B) of cb.tail_feat (half_off == 0) / cb.tail_grad instead of gathering.
+template <int VEC, bool HAS_GQ, bool WIDE, bool DENSE_TAIL = false>
 __device__ __forceinline__ void gather_accumulate(const EntryGroup& g, int B, const float* __restrict__ dense,
                                                   int64_t ldd, const Codebook& cb, int half_off, float tscale,
                                                   int c0, int k, int off, float (&acc)[VEC], float (&gqa)[VEC]) {
   constexpr int U = kMpUnroll;
   const float* p[U];
-  const float* tdense = half_off == 0 ? cb.tail_feat : cb.tail_grad;  // uniform: dense tail rows available?
-  if (!WIDE && !HAS_GQ && tdense != nullptr) {
+  if constexpr (DENSE_TAIL) {   // tail rows were materialised (vqgnn_tail_materialize): plain coalesced row reads
+    static_assert(!WIDE && !HAS_GQ, "dense tail rows carry one half only");
+    const float* tdense = half_off == 0 ? cb.tail_feat : cb.tail_grad;
     float a[U][VEC];
 #pragma unroll
     for (int u = 0; u < U; ++u) {

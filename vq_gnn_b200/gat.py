@@ -30,10 +30,21 @@ class VQGATFunction(torch.autograd.Function):
         assert al.numel() == C + 1 and ar.numel() == C + 1
         a_l, a_r = torch.empty(R, device=dev), torch.empty(R, device=dev)
         stat = torch.empty(2, device=dev)
+        tail_feat = tail_grad = None
+        auto = bank.M * bank.nb * 32 > (2 << 20) and plan.nnz >= 8 * max(plan.T, 1)
+        if (plan.T > 0 and bank.D == 4 and bank.Wp == 8
+                and (layer.materialize_tail == 'force' or (layer.materialize_tail and auto))):
+            # every out-of-batch node's codewords gathered once into dense rows (see models.VQConvFunction)
+            tail_feat = torch.empty(plan.T, C, device=dev)
+            tail_grad = torch.empty(plan.T, C, device=dev) if plan.training else None
+            _lib.check(lib.vqgnn_tail_materialize(
+                _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
+                bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, st))
+        ctx.tail = (tail_feat, tail_grad)
         _lib.check(lib.vqgnn_gat_scores(
             R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O),
-            bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r),
-            _lib.ptr(stat), st))
+            bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C, _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l),
+            _lib.ptr(a_r), _lib.ptr(stat), st))
         y = torch.empty(B, C, device=dev)
         den = torch.empty(B, device=dev)
         need_info = plan.training
@@ -43,8 +54,8 @@ class VQGATFunction(torch.autograd.Function):
             _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
             _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, R, B, _lib.ptr(x), x.stride(0),
             _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
-            _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), float(slope), float(wu), _lib.ptr(y), y.stride(0),
-            _lib.ptr(den), _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+            _lib.ptr(tail_feat), C, _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), float(slope), float(wu),
+            _lib.ptr(y), y.stride(0), _lib.ptr(den), _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
         ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook, ctx.slope = layer, plan, float(wu), fire_hook, float(slope)
         ctx.att_shape = att_l.shape
         ctx.save_for_backward(x, al, ar, a_l, a_r, stat, y, den)
@@ -71,6 +82,7 @@ class VQGATFunction(torch.autograd.Function):
             _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
             _lib.ptr(plan.chunk_rows('bwd')), int(plan.bwd_col.numel()), MP_CHUNK, B, _lib.ptr(x), x.stride(0),
             _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
+            _lib.ptr(ctx.tail[0]), _lib.ptr(ctx.tail[1]), C,
             _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), ctx.slope,
             _lib.ptr(y), y.stride(0), _lib.ptr(den), _lib.ptr(dy), dy.stride(0), wu, _lib.ptr(dinfo),
             _lib.ptr(dyn), dyn.stride(0), _lib.ptr(dden), _lib.ptr(ds_l), _lib.ptr(ds_r),
