@@ -80,6 +80,8 @@ def main():
         torch.manual_seed(0)
         layer = V.LowRankGNNLayer(*H.layer_args(C, C, s["M"], 4, s["N"], s["conv"], skip=False),
                                   version=s["version"]).to(dev).train()
+        if os.environ.get("VQGNN_MATERIALIZE"):
+            layer.materialize_tail = {"force": "force", "0": False}.get(os.environ["VQGNN_MATERIALIZE"], True)
         impl = os.environ.get("VQGNN_ASSIGN_IMPL", "auto")
         layer.bank.assign_impl = impl if impl == "auto" else int(impl)
         plan = V.build_plan(bA, s["conv"], s["N"], True, dev).warm()

@@ -31,7 +31,7 @@ class VQGATFunction(torch.autograd.Function):
         a_l, a_r = torch.empty(R, device=dev), torch.empty(R, device=dev)
         stat = torch.empty(2, device=dev)
         tail_feat = tail_grad = None
-        auto = bank.M * bank.nb * 32 > (2 << 20) and plan.nnz >= 8 * max(plan.T, 1)
+        auto = plan.nnz >= 4 * max(plan.T, 1)
         if (plan.T > 0 and bank.D == 4 and bank.Wp == 8
                 and (layer.materialize_tail == 'force' or (layer.materialize_tail and auto))):
             # every out-of-batch node's codewords gathered once into dense rows (see models.VQConvFunction)
