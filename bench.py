@@ -520,9 +520,8 @@ def main():
                 traffic = sum(tj["per_launch_bytes"]) / len(tj["per_launch_bytes"])
         roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                     "frac": achieved / peak, "traffic": traffic,
-                    "traffic_note": "ncu dram bytes per launch at batch 0 (2.93 M tail entries; the timed batches "
-                                    "average 4.6 M); below the algorithmic bytes because the code table is partly "
-                                    "L2-resident" if traffic else None,
+                    "traffic_note": "ncu dram bytes per launch, averaged over the three layer launches of one 5.1 M-entry "
+                                    "batch; below the algorithmic bytes because the code table is partly L2-resident" if traffic else None,
                     "peak_source": pk["source"],
                     "avg_launch_ms": avg_ms, "launches_per_step": n_launch / n_attr,
                     "algorithmic_work_per_launch": per_launch_work}
