@@ -328,6 +328,9 @@ def main():
         train_step(model, opt, x, plans[i % len(plans)], y, distributed)
     sync_all()
 
+    sampler = ClockSampler(local_rank)     # nvidia-smi every 100 ms across BOTH timed regions (e2e + device-resident)
+    sampler.start()
+
     # ---- end-to-end through the public API from pinned host buffers (eager; measured BEFORE the CUDA graphs of
     #      the device-resident timing exist: their private memory pools slow later eager allocation down) ----
     host = []
@@ -438,8 +441,6 @@ def main():
             x, _, y = batches[i % len(batches)]
             train_step(model, opt, x, plans[i % len(plans)], y, distributed)
     sync_all()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()

@@ -73,7 +73,8 @@ def main():
            "cases": {}}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _lib.load()
-    for name in ("c1_arxiv", "c2_reddit", "c3_ppi", "c4_collab", "c5_products"):
+    cases = os.environ.get("VQGNN_CASES", "c1_arxiv,c2_reddit,c3_ppi,c4_collab,c5_products").split(",")
+    for name in cases:
         t0 = time.time()
         s, nodes, bA, C = make_case(name, dev)
         B = int(nodes.numel())
