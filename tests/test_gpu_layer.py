@@ -269,3 +269,21 @@ def test_device_plan_builder_matches_torch_builder(conv, train, recovery):
     n_tail = int(sp['tail'][6].item())
     assert n_tail == int((p_t.fwd_col >= B).sum())
     assert int(sp['tail'][0][-1]) == n_tail and torch.equal(p_t.bwd_rowptr, p_d.bwd_rowptr)
+
+
+@pytest.mark.parametrize("C", [8, 5, 132])
+def test_plain_conv_forward_matches_oracle(C):
+    """OurGCNConv / OurGATConv.forward on an explicit adjacency (no codeword rows): convs.py:65-101, 165-266."""
+    dev = torch.device("cuda:0")
+    n = 300
+    g = H.make_graph(n, 3000, "GAT", "v2", seed=5)
+    from vq_gnn_b200.graph import CSRAdj
+    adj = CSRAdj(g.rowptr, g.col, g.val, (n, n))
+    x = torch.randn(n, C, generator=torch.Generator().manual_seed(1))
+    dense = adj.to_dense()
+    gcn = V.OurGCNConv(C, C, normalize=False)
+    assert H.rel_err(gcn(x.to(dev), adj.to(dev)), restate.gcn_propagate(dense, x)) < REL_TOL
+    torch.manual_seed(2)
+    gat = V.OurGATConv(C, C, bias=False, add_self_loops=False).to(dev)
+    want = restate.gat_propagate(dense, x, gat.att_l.detach().cpu().view(-1), gat.att_r.detach().cpu().view(-1))
+    assert H.rel_err(gat(x.to(dev), adj.to(dev)), want) < REL_TOL

@@ -90,7 +90,7 @@ class OurGATConv(nn.Module):
         if isinstance(edge_index, torch.Tensor):
             raise NotImplementedError  # vq_softmax.py:54-55: only the CSR (SparseTensor) path exists
         from .models import plain_propagate
-        return plain_propagate(x, edge_index, self.att_l.view(-1), self.att_r.view(-1))
+        return plain_propagate(x, edge_index, self.att_l.view(-1), self.att_r.view(-1), self.negative_slope)
 
 
 class Transformer(nn.Module):

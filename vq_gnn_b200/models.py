@@ -146,12 +146,14 @@ class VQConvFunction(torch.autograd.Function):
         return dx, None, None, None, None, None
 
 
-def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Tensor]) -> Tensor:
-    """`conv.forward(x, adj)` of the reference on an explicit adjacency with no codeword rows."""
+def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Tensor],
+                    negative_slope: float = 0.2) -> Tensor:
+    """`conv.forward(x, adj)` of the reference on an explicit adjacency with no codeword rows (forward only):
+    GCN/SAGE  out = adj @ x                                                        (convs.py:65-101)
+    GAT       out[i] = sum_j adj[i,j] exp(lrelu((a_l[j] + a_r[i]) / sigma)) x[j]   (convs.py:165-266), all columns
+              of x taking part in the scores (att_* of length C) -- the un-normalised sum the reference returns."""
     _lib.require_device(x)
     n = x.shape[0]
-    if att_l is not None:
-        raise NotImplementedError("plain GAT propagate lands with the GAT kernels")
     rowptr, col, val = adj.csr()
     assert int(adj.sparse_sizes()[0]) == n
     C = x.shape[1]
@@ -165,11 +167,28 @@ def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Ten
     nnz = int(col.numel())
     chunks = torch.empty(max(int(lib.vqgnn_mp_num_chunks(nnz, MP_CHUNK)), 1), dtype=torch.int32, device=x.device)
     _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(rowptr), n, nnz, MP_CHUNK, _lib.ptr(chunks), st))
-    _lib.check(lib.vqgnn_mp_fwd(
-        _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), None, _lib.ptr(chunks), MP_CHUNK, nnz,
-        n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, None, 0, 1.0, 1.0,
-        _lib.ptr(y), y.stride(0), None, 0, None, None, st))
-    return y
+    if att_l is None:
+        _lib.check(lib.vqgnn_mp_fwd(
+            _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), None, _lib.ptr(chunks), MP_CHUNK, nnz,
+            n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, None, 0, 1.0, 1.0,
+            _lib.ptr(y), y.stride(0), None, 0, None, None, st))
+        return y
+    # GAT: the fused kernels carry an implicit ones column (coefficient att[C]); a zero coefficient removes it from
+    # the scores, and multiplying the normalised output back by its denominator gives the reference's plain sum
+    zero = torch.zeros(1, device=x.device)
+    al = torch.cat([att_l.detach().reshape(-1).float(), zero])
+    ar = torch.cat([att_r.detach().reshape(-1).float(), zero])
+    assert al.numel() == C + 1, "att_l / att_r must have one entry per column of x"
+    a_l, a_r, stat = torch.empty(n, device=x.device), torch.empty(n, device=x.device), torch.empty(2, device=x.device)
+    den = torch.empty(n, device=x.device)
+    _lib.check(lib.vqgnn_gat_scores(n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D,
+                                    8, None, 0, _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r),
+                                    _lib.ptr(stat), st))
+    _lib.check(lib.vqgnn_gat_fwd(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(chunks), MP_CHUNK, nnz, n, n,
+                                 _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8,
+                                 None, 0, _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), float(negative_slope), 1.0,
+                                 _lib.ptr(y), y.stride(0), _lib.ptr(den), None, None, st))
+    return y * (den + 1e-16).unsqueeze(1)
 
 
 # --------------------------------------------------------------------------------------------------
