@@ -175,6 +175,13 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
  *       *info += info_scale * sum_r <x[r], gq contribution>               (info must be zero-initialised)
  *   d_nnz != NULL: the entry count lives on the device (vqgnn_plan_v1_build); nnz is then its upper bound. */
 int vqgnn_mp_tail_group(int M, int D, int Wp);
+/* Apply n (node, codes[nbc]) updates for branches [k0, k0 + nbc) to codes [N, nb] (and its group-major mirror
+ * codes_g when not NULL); when a node is listed more than once the LAST entry wins.  Multi-GPU: the list is the
+ * rank-ordered all-gather of every rank's re-assignments, so every replica ends up identical.
+ * owner_ws: N int32 of scratch. */
+int vqgnn_codes_apply_updates(const int32_t* nodes, const int16_t* new_codes, int64_t n, int nbc, int k0,
+                              int16_t* codes, int nb, int64_t N, int16_t* codes_g, int G, int32_t* owner_ws,
+                              void* stream);
 int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* rows, int64_t n_rows, int64_t N, int G,
                       int16_t* codes_g, void* stream);
 int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* val, const float* rval,

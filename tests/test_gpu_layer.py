@@ -287,3 +287,28 @@ def test_plain_conv_forward_matches_oracle(C):
     gat = V.OurGATConv(C, C, bias=False, add_self_loops=False).to(dev)
     want = restate.gat_propagate(dense, x, gat.att_l.detach().cpu().view(-1), gat.att_r.detach().cpu().view(-1))
     assert H.rel_err(gat(x.to(dev), adj.to(dev)), want) < REL_TOL
+
+
+def test_codes_apply_updates_last_entry_wins():
+    """vqgnn_codes_apply_updates (the multi-GPU code-table update) vs its torch restatement, with repeated nodes."""
+    from vq_gnn_b200 import _lib, dist as vdist
+    dev = torch.device("cuda:0")
+    lib, st = _lib.load(), _lib.stream()
+    N, nb, n, k0, nbc, G = 5000, 14, 6000, 0, 14, 6
+    gen = torch.Generator().manual_seed(3)
+    nodes = torch.randint(0, N, (n,), generator=gen, dtype=torch.int32)          # many repeats
+    new = torch.randint(0, 1024, (n, nbc), generator=gen, dtype=torch.int16)
+    codes0 = torch.randint(0, 1024, (N, nb), generator=gen, dtype=torch.int16)
+    want = codes0.clone()
+    vdist.apply_code_updates_(want, nodes, new, k0)
+    codes = codes0.clone().to(dev)
+    ng = (nb + G - 1) // G
+    codes_g = torch.zeros(ng, N, 8, dtype=torch.int16, device=dev)
+    _lib.check(lib.vqgnn_codes_group(_lib.ptr(codes), nb, None, N, N, G, _lib.ptr(codes_g), st))
+    owner = torch.empty(N, dtype=torch.int32, device=dev)
+    nd, nw = nodes.to(dev), new.to(dev)
+    _lib.check(lib.vqgnn_codes_apply_updates(_lib.ptr(nd), _lib.ptr(nw), n, nbc, k0, _lib.ptr(codes), nb, N,
+                                             _lib.ptr(codes_g), G, _lib.ptr(owner), st))
+    assert torch.equal(codes.cpu(), want)
+    for k in range(nb):
+        assert torch.equal(codes_g[k // G, :, k % G].cpu(), want[:, k])

@@ -266,9 +266,59 @@ __global__ void codes_group_kernel(const int16_t* __restrict__ codes, int nb, co
   }
 }
 
+// Apply a list of (node, codes) updates to the code table with LAST-ENTRY-WINS semantics for repeated nodes
+// (multi-GPU: the list is the all-gather of every rank's re-assignments in rank order, so every replica resolves
+// a node shared by two ranks' batches identically).  owner[node] = index of the last entry naming the node.
+__global__ void codes_owner_kernel(const int32_t* __restrict__ nodes, int64_t n, int32_t* __restrict__ owner,
+                                   int phase) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const int32_t nd = __ldg(nodes + e);
+    if (phase == 0) owner[nd] = -1;
+    else atomicMax(owner + nd, static_cast<int32_t>(e));
+  }
+}
+__global__ void codes_apply_kernel(const int32_t* __restrict__ nodes, const int16_t* __restrict__ new_codes,
+                                   int64_t n, int nbc, int k0, const int32_t* __restrict__ owner,
+                                   int16_t* __restrict__ codes, int nb, int64_t N, int16_t* __restrict__ codes_g,
+                                   int G) {
+  const int64_t total = n * nbc;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t e = i / nbc;
+    const int j = static_cast<int>(i - e * nbc);
+    const int64_t nd = __ldg(nodes + e);
+    if (__ldg(owner + nd) != e) continue;
+    const int k = k0 + j;
+    const int16_t cv = __ldg(new_codes + i);
+    codes[nd * nb + k] = cv;
+    if (codes_g) codes_g[((static_cast<int64_t>(k / G)) * N + nd) * 8 + (k % G)] = cv;
+  }
+}
+
 }  // namespace vqgnn
 
 using namespace vqgnn;
+
+extern "C" int vqgnn_codes_apply_updates(const int32_t* nodes, const int16_t* new_codes, int64_t n, int nbc, int k0,
+                                         int16_t* codes, int nb, int64_t N, int16_t* codes_g, int G,
+                                         int32_t* owner_ws, void* stream) {
+  VQ_CHECK_ARG(nodes && new_codes && codes && owner_ws && n >= 0 && n < (1ll << 31) && nbc > 0 && k0 >= 0 &&
+                   k0 + nbc <= nb && N > 0,
+               "codes_apply_updates: bad arguments");
+  VQ_CHECK_ARG(!codes_g || G == 6 || G == 8, "codes_apply_updates: bad group size");
+  if (n == 0) return VQGNN_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g1 = static_cast<int>(std::min<int64_t>((n + 255) / 256, 8 * kNumSMs));
+  codes_owner_kernel<<<g1, 256, 0, s>>>(nodes, n, owner_ws, 0);
+  VQ_LAUNCH_CHECK();
+  codes_owner_kernel<<<g1, 256, 0, s>>>(nodes, n, owner_ws, 1);
+  VQ_LAUNCH_CHECK();
+  const int g2 = static_cast<int>(std::min<int64_t>((n * nbc + 255) / 256, 16 * kNumSMs));
+  codes_apply_kernel<<<g2, 256, 0, s>>>(nodes, new_codes, n, nbc, k0, owner_ws, codes, nb, N, codes_g, G);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}
 
 extern "C" int vqgnn_mp_tail_group(int M, int D, int Wp) {
   if (D != 4 || Wp != 8 || M <= 0) return 0;

@@ -67,13 +67,9 @@ def allreduce_mean_grads_(params: Iterable[Tensor], group=None) -> None:
         off += g.numel()
 
 
-def allgather_code_updates_(codes: Tensor, batch_idx: Tensor, new_codes: Tensor, k0: int = 0, group=None):
-    """Apply every OTHER rank's code-table updates to this rank's replica.
-
-    codes [N, nb] int16 is the local replica (already holding this rank's own update), batch_idx [B] the global
-    node ids this rank just re-assigned, new_codes [B, nbc] their codes for branches [k0, k0 + nbc).  Ranks are
-    applied in rank order, so when two ranks' batches share a node every replica ends with the same (highest
-    rank's) code.  Returns the gathered node ids [world * B] (for the group-major mirror), or None when single."""
+def allgather_code_updates(batch_idx: Tensor, new_codes: Tensor, group=None):
+    """All-gather, in rank order, every rank's (re-assigned node ids [B], their new codes [B, nbc]) ->
+    (gidx [world * B], gcodes [world * B, nbc]), or None for a single process."""
     rank, ws = world(group)
     if ws == 1:
         return None
@@ -84,10 +80,27 @@ def allgather_code_updates_(codes: Tensor, batch_idx: Tensor, new_codes: Tensor,
     _timed("nccl_allgather_codes", lambda: (
         dist.all_gather_into_tensor(gidx, batch_idx.contiguous(), group=group),
         dist.all_gather_into_tensor(gcodes.view(torch.uint8), new_codes.contiguous().view(torch.uint8), group=group)))
-    for r in range(ws):      # rank order => identical result on every replica (own slice included on purpose)
-        sl = slice(r * B, (r + 1) * B)
-        codes[gidx[sl].long(), k0:k0 + nbc] = gcodes[sl]
-    return gidx
+    return gidx, gcodes
+
+
+def apply_code_updates_(codes: Tensor, gidx: Tensor, gcodes: Tensor, k0: int = 0) -> None:
+    """Plain-torch application of gathered updates, LAST entry wins for a repeated node (so a node shared by two
+    ranks' batches resolves identically on every replica).  The CUDA path uses vqgnn_codes_apply_updates; this is
+    its device-agnostic restatement (CPU tests, fallback for odd dtypes)."""
+    n, nbc = gcodes.shape
+    owner = torch.full((codes.shape[0],), -1, dtype=torch.long, device=codes.device)
+    owner.scatter_reduce_(0, gidx.long(), torch.arange(n, device=codes.device), reduce='amax')
+    win = owner[gidx.long()] == torch.arange(n, device=codes.device)
+    codes[gidx[win].long(), k0:k0 + nbc] = gcodes[win]
+
+
+def allgather_code_updates_(codes: Tensor, batch_idx: Tensor, new_codes: Tensor, k0: int = 0, group=None):
+    """Gather + apply (see the two functions above).  Returns the gathered node ids or None when single."""
+    got = allgather_code_updates(batch_idx, new_codes, group)
+    if got is None:
+        return None
+    apply_code_updates_(codes, got[0], got[1], k0)
+    return got[0]
 
 
 def replicas_max_abs_diff(t: Tensor, group=None) -> float:

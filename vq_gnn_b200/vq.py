@@ -68,6 +68,7 @@ class VQBank:
         self.G = 0                   # branches per group; resolved on the device (vqgnn_mp_tail_group)
         self.codes_g: Optional[Tensor] = None
         self._codes_g_dirty = True
+        self._owner_ws: Optional[Tensor] = None     # scratch of vqgnn_codes_apply_updates (multi-GPU)
 
     TENSORS = ("E", "O", "Wm", "size", "rm_f", "rv_f", "rm_g", "rv_g", "nbt_f", "nbt_g", "codes", "status")
 
@@ -182,16 +183,23 @@ class VQBank:
                 1 if self.warm_up_flag else 0, self.eps, self.scale[0], self.scale[1], _lib.ptr(rm_f),
                 _lib.ptr(rv_f), _lib.ptr(rm_g) if joint else None, _lib.ptr(rv_g) if joint else None,
                 _lib.ptr(size), _lib.ptr(Wm), _lib.ptr(E), _lib.ptr(O), _lib.ptr(self.status), st))
-        touched, n_touched = bidx, B
         if codes_ptr is not None and self.distributed:
             # every replica of the code table learns the other ranks' re-assignments (their batch nodes are this
-            # rank's out-of-batch neighbours): one all-gather of (node id, codes) per update
-            gidx = dist.allgather_code_updates_(self.codes, bidx, idx, k0, self.process_group)
-            if gidx is not None:
-                touched, n_touched = gidx, int(gidx.numel())
-        if codes_ptr is not None and self.codes_g is not None and not self._codes_g_dirty:
+            # rank's out-of-batch neighbours): one all-gather of (node id, codes) per update, applied by one kernel
+            # with last-entry-wins semantics (identical on every rank)
+            got = dist.allgather_code_updates(bidx, idx, self.process_group)
+            if got is not None:
+                gidx, gcodes = got
+                if self._owner_ws is None or self._owner_ws.device != dev:
+                    self._owner_ws = torch.empty(self.codes.shape[0], dtype=torch.int32, device=dev)
+                mirror = self.codes_g if (self.codes_g is not None and not self._codes_g_dirty) else None
+                _lib.check(lib.vqgnn_codes_apply_updates(
+                    _lib.ptr(gidx), _lib.ptr(gcodes), int(gidx.numel()), nbc, k0, _lib.ptr(self.codes), self.nb,
+                    self.codes.shape[0], _lib.ptr(mirror), max(self.G, 0) if mirror is not None else 0,
+                    _lib.ptr(self._owner_ws), st))
+        elif codes_ptr is not None and self.codes_g is not None and not self._codes_g_dirty:
             if k0 == 0 and nbc == self.nb:    # keep the group-major mirror in step (re-assigned rows only)
-                _lib.check(lib.vqgnn_codes_group(_lib.ptr(self.codes), self.nb, _lib.ptr(touched), n_touched,
+                _lib.check(lib.vqgnn_codes_group(_lib.ptr(self.codes), self.nb, _lib.ptr(bidx), B,
                                                  self.codes.shape[0], self.G, _lib.ptr(self.codes_g), st))
             else:
                 self._codes_g_dirty = True
