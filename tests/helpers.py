@@ -57,7 +57,7 @@ def att_grad_err(got: dict, want: dict):
     """Error of the GAT attention-vector gradients, relative to their JOINT scale.  "Trick 1" (convs.py:209-211)
     makes the scores invariant to a rescaling of att_l (att_r) when max|a_l| >> 1, so the gradient along
     att_l is a difference of large terms: in fp32 the reference itself moves by ~1e-3 of |d att_l| between
-    CPU and GPU (scripts/debug_gat_att_grad.py), while it is stable to ~1e-6 of the joint (att_l, att_r) gradient."""
+    CPU and GPU (tests/debug_gat_att_grad.py), while it is stable to ~1e-6 of the joint (att_l, att_r) gradient."""
     keys = [k for k in want if "att_" in k and k in got]
     if not keys:
         return 0.0
