@@ -232,7 +232,8 @@ MP_CHUNK = 256   # CSR entries per warp task (multiple of 32)
 
 
 DEVICE_PLAN_BUILDER = True   # v1 plans on CUDA are built by csrc/plan.cu (False: the torch builder below)
-TAIL_CHUNK = 512  # entries per warp task of the shared-memory tail kernel (csrc/mp_tail.cu)
+import os as _os
+TAIL_CHUNK = int(_os.environ.get('VQGNN_TAIL_CHUNK', '512'))  # entries per warp task of the shared-memory tail kernel (csrc/mp_tail.cu)
 TAIL_MIN_AVG_DEGREE = 32   # below this the per-row reduce of the lane=entry kernel does not pay
 
 
