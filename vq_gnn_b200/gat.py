@@ -80,7 +80,7 @@ class VQGATFunction(torch.autograd.Function):
             _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
             _lib.ptr(plan.chunk_rows('fwd')), plan.nnz, R,
             _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
-            _lib.ptr(plan.chunk_rows('bwd')), int(plan.bwd_col.numel()), MP_CHUNK, B, _lib.ptr(x), x.stride(0),
+            _lib.ptr(plan.chunk_rows('bwd')), int(plan.bwd_col.numel()), plan.small_chunk, B, _lib.ptr(x), x.stride(0),
             _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
             _lib.ptr(ctx.tail[0]), _lib.ptr(ctx.tail[1]), C,
             _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat), ctx.slope,

@@ -112,6 +112,9 @@ class BatchPlan:
         self.extras = {} if extras is None else extras
         self._nnz = nnz
         self._has_rval = has_rval
+        # v1: the in-batch block (forward split + transposed CSR) is small (~2 x 10^5 entries at the Reddit shape);
+        # finer chunks give its kernels enough warps to fill the machine
+        self.small_chunk = small_chunk(int(bwd_col.numel())) if version == 'v1' else MP_CHUNK
 
     def _merged(self):
         if self._fwd is None:
@@ -167,11 +170,12 @@ class BatchPlan:
                 nnz, rows = self.nnz, self.R
             else:
                 rowptr, nnz, rows = self.bwd_rowptr, int(self.bwd_col.numel()), self.B
+            chunk = MP_CHUNK if which == 'fwd' else self.small_chunk
             _lib.require_device(rowptr)
             lib = _lib.load()
-            n = int(lib.vqgnn_mp_num_chunks(nnz, MP_CHUNK))
+            n = int(lib.vqgnn_mp_num_chunks(nnz, chunk))
             t = torch.empty(max(n, 1), dtype=torch.int32, device=rowptr.device)
-            _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(rowptr), rows, nnz, MP_CHUNK, _lib.ptr(t), _lib.stream()))
+            _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(rowptr), rows, nnz, chunk, _lib.ptr(t), _lib.stream()))
             self.extras[key] = t
         return t
 
@@ -223,12 +227,17 @@ class BatchPlan:
             iptr, icol, ival = raw['inb']
             tn, inn = int(tnode.numel()), int(icol.numel())
             sp = dict(tail=(tptr, tnode, tval, trval, chunks(tptr, tn, TAIL_CHUNK), tn),
-                      inb=(iptr, icol, ival, chunks(iptr, inn, MP_CHUNK), inn))
+                      inb=(iptr, icol, ival, chunks(iptr, inn, self.small_chunk), inn))
             self.extras['split'] = sp
         return sp
 
 
 MP_CHUNK = 256   # CSR entries per warp task (multiple of 32)
+
+
+def small_chunk(nnz: int) -> int:
+    """Chunk size for a small CSR: 64 entries per warp task below 2^20 entries."""
+    return 64 if nnz < (1 << 20) else MP_CHUNK
 
 
 DEVICE_PLAN_BUILDER = True   # v1 plans on CUDA are built by csrc/plan.cu (False: the torch builder below)
@@ -316,14 +325,15 @@ def plan_from_v1_device(batch_A, conv_type: str, N: int, training: bool, device)
     i32 = lambda n: torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     f32 = lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=dev)
     n_tc = int(lib.vqgnn_mp_num_chunks(nnz, TAIL_CHUNK))
-    n_ic = int(lib.vqgnn_mp_num_chunks(nin, MP_CHUNK))
+    ichunk = small_chunk(nin)
+    n_ic = int(lib.vqgnn_mp_num_chunks(nin, ichunk))
     tptr, tnode, tval, trval, tcount, tcr = i32(B + 1), i32(nnz), f32(nnz), f32(nnz), i32(1), i32(n_tc)
     iptr, icol, ival, icr = i32(B + 1), i32(nin), f32(nin), i32(n_ic)
     bptr, brow, bval, bcr = i32(B + 1), i32(nin), f32(nin), i32(n_ic)
     ws = torch.empty(int(lib.vqgnn_plan_v1_workspace_bytes(N, B)), dtype=torch.uint8, device=dev)
     _lib.check(lib.vqgnn_plan_v1_build(
         _lib.ptr(r), _lib.ptr(c), _lib.ptr(v), _lib.ptr(rv), nnz, _lib.ptr(br), _lib.ptr(bc), _lib.ptr(bv), nbb,
-        _lib.ptr(bidx), _lib.ptr(dinv), B, N, sym, loops, TAIL_CHUNK, MP_CHUNK,
+        _lib.ptr(bidx), _lib.ptr(dinv), B, N, sym, loops, TAIL_CHUNK, ichunk,
         _lib.ptr(tptr), _lib.ptr(tnode), _lib.ptr(tval), _lib.ptr(trval), _lib.ptr(tcount), _lib.ptr(tcr),
         _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), _lib.ptr(icr),
         _lib.ptr(bptr), _lib.ptr(brow), _lib.ptr(bval), _lib.ptr(bcr), _lib.ptr(ws), st))

@@ -85,7 +85,7 @@ class VQConvFunction(torch.autograd.Function):
             tptr, tnode, tval, trval, tcr, tnnz = sp['tail'][:6]
             tcount = sp['tail'][6] if len(sp['tail']) > 6 else None   # entry count on the device (plan.cu)
             _lib.check(lib.vqgnn_mp_fwd(
-                _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), None, _lib.ptr(icr), MP_CHUNK, innz, B, B,
+                _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), None, _lib.ptr(icr), plan.small_chunk, innz, B, B,
                 _lib.ptr(x), x.stride(0), None, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
                 bank.Wp, None, 0, 1.0, 1.0, _lib.ptr(y), y.stride(0), None, 0, None, None, st))
             gq.zero_()
@@ -136,7 +136,7 @@ class VQConvFunction(torch.autograd.Function):
             dx = torch.empty(B, C, device=x.device)
             _lib.check(lib.vqgnn_mp_bwd(
                 _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
-                _lib.ptr(plan.chunk_rows('bwd')), MP_CHUNK, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
+                _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
                 dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
                 bank.M, bank.D, bank.Wp, _lib.ptr(ctx.tail_grad), C, 0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
                 wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0), st))
