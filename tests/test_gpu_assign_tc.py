@@ -67,3 +67,31 @@ def test_tcgen05_assignment_matches_fp32(B, nb, M, D, joint, add):
     if n_diff == 0:
         assert torch.equal(s0[:, :, Wp], s1[:, :, Wp])                    # counts bit-exact
         assert float((s0 - s1).abs().max()) <= 1e-4 * float(s0.abs().max())
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_exact_ties_pick_the_lowest_index(impl):
+    """Duplicate codewords give bit-identical distances; torch.argmin (vq.py:171,236) returns the first, and so must
+    both kernels -- including across the tcgen05 kernel's 256-codeword tiles and 64-column epilogue quarters."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(9)
+    B, nb, M, D = 700, 3, 1024, 4
+    x = torch.randn(B, nb * D, generator=gen, device=dev)
+    g = torch.randn(B, nb * D, generator=gen, device=dev)
+    base = torch.randn(nb, 64, 8, generator=gen, device=dev)
+    E = base.repeat(1, M // 64, 1).contiguous()          # every codeword appears 16 times, 64 apart
+    idx, _ = _assign(x, g, E, M, D, D, impl, with_stats=False)
+    assert int(idx.max()) < 64, int(idx.max())           # always the first copy
+    ref, _ = _assign(x, g, base.contiguous(), 64, D, D, 0, with_stats=False)
+    assert torch.equal(idx, ref)
+
+
+def test_rows_not_a_multiple_of_the_tile_and_single_row():
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(4)
+    for B in (1, 127, 129):
+        x = torch.randn(B, 8, generator=gen, device=dev)
+        E = torch.randn(2, 512, 8, generator=gen, device=dev)
+        i0, s0 = _assign(x, None, E, 512, 4, 4, 0)
+        i1, s1 = _assign(x, None, E, 512, 4, 4, 1)
+        assert torch.equal(i0, i1) and torch.equal(s0[:, :, 8], s1[:, :, 8])
