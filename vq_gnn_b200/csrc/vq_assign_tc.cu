@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int k = static_cast<int>(item / row_tiles);
       const int64_t b = (item - static_cast<int64_t>(k) * row_tiles) * kTileM + rl;
       load_raw(item + 2, z2);
+      // the code-table row this thread will write at the end of the item: fetch its index now, not on the tail
+      const int32_t my_node = (codes && h == 0 && b < B) ? __ldg(batch_idx + b) : 0;
       whiten(item + 1, z1);          // its loads were issued one whole item ago
       if (item + 1 < item_end) stage_a(it + 1, z1);
 
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
         const int code = besti;
         if (idx) idx[b * nb + k] = static_cast<int16_t>(code);
-        if (codes) codes[static_cast<int64_t>(__ldg(batch_idx + b)) * codes_ld + k] = static_cast<int16_t>(code);
+        if (codes) codes[static_cast<int64_t>(my_node) * codes_ld + k] = static_cast<int16_t>(code);
         if (stats) {
           float* dst = stats + (static_cast<int64_t>(k) * M + code) * (Wp + 4);
 #pragma unroll
