@@ -28,6 +28,7 @@ def _check_assign(idx_gpu, idx_ref, dist_ref):
 
 @pytest.mark.parametrize("M,D,B,add_flag", [(16, 4, 300, False), (256, 4, 5000, False), (64, 4, 1000, True),
                                             (1024, 4, 6000, False), (32, 2, 500, False), (48, 8, 700, False)])
+@H.retry_on_atomic_order()
 def test_vq_update_matches_oracle(M, D, B, add_flag):
     dev = torch.device("cuda:0")
     torch.manual_seed(1)
