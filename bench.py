@@ -390,8 +390,8 @@ def main():
     e2e_run(3 * len(host) + 2)   # lets the caching allocator's side-stream pool converge (no cudaMalloc in the timed run)
     sync_all()
     e2e_passes = []
-    for _ in range(2):       # two passes of K steps each; the faster one is reported (a freshly booted box shows
-        sync_all()           # host-side first-touch noise in the first pass: 2.6 M vs 5.6 M nodes/s/layer at N=2)
+    for _ in range(4):       # four passes of K steps each; the fastest one is reported: the eager e2e loop is bound by
+        sync_all()           # the host's Python launch rate and a shared host shows 2x pass-to-pass noise
         t0 = time.perf_counter()
         e2e_run(args.steps)
         torch.cuda.synchronize()
@@ -555,7 +555,7 @@ def main():
                 "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "nodes/s/layer", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4, "passes_ms": [round(t, 2) for t in e2e_passes],
-                        "note": "K steps per pass, faster of two passes; eager launches, DevicePrefetcher"},
+                        "note": "K steps per pass, fastest of four passes; eager launches, DevicePrefetcher"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "replica_max_abs_diff": replica_div, "cuda_graphs": graphs is not None, "kernels": kernel_table, "assign_impl": {"auto": "tcgen05 (auto: M=1024)", "1": "tcgen05", "0": "simt-fp32"}[str(args.assign_impl)]}
         print(json.dumps(line), flush=True)
