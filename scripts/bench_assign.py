@@ -1,7 +1,6 @@
 import sys; sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import torch
 from tests.test_gpu_assign_tc import _assign
-from vq_gnn_b200 import _lib
 dev = torch.device("cuda:0")
 def timeit(B, nb, M, impl, with_stats, reps=5):
     gen = torch.Generator(device=dev).manual_seed(0)

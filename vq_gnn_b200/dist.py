@@ -10,7 +10,7 @@ The reference has no distributed code; the design is SURVEY.md 
 """
 from __future__ import annotations
 
-from typing import Iterable, Optional, Tuple
+from typing import Iterable, Tuple
 
 import torch
 import torch.distributed as dist

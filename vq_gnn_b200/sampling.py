@@ -9,7 +9,7 @@ The order of the B' nodes is unspecified in the reference (`unique(sorted=False)
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 

@@ -15,7 +15,7 @@ every rank's codebook replica identical.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 from torch import nn
