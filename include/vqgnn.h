@@ -210,6 +210,15 @@ int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, cons
                         int32_t* i_col, float* i_val, int32_t* i_chunk_row, int32_t* b_rowptr, int32_t* b_row,
                         float* b_val, int32_t* b_chunk_row, void* ws, void* stream);
 
+/* Transposed CSR restricted to columns < B of a CSR over R rows (the backward structure of a v2 batch graph):
+ * browptr [B+1], brow / bval sized nnz (upper bound; the first *count entries are valid, order inside a column is
+ * free), *count = number of entries with col < B (stays on the device: read it back lazily).
+ * ws: vqgnn_csr_transpose_workspace_bytes(B). */
+size_t vqgnn_csr_transpose_workspace_bytes(int64_t B);
+int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col, const float* val, int64_t R, int64_t nnz,
+                           int64_t B, int32_t* browptr, int32_t* brow, float* bval, int32_t* count, void* ws,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Message passing, GAT, v2 ("B+B'") formulation: OurGATConv.forward/message (vq_gnn_v2/convs.py:165-266)
  * with vq_softmax == un-normalised exp (vq_gnn_v2/utils/vq_softmax.py:41-57), fused with the codeword

@@ -318,3 +318,26 @@ def test_codes_apply_updates_last_entry_wins():
     assert torch.equal(codes.cpu(), want)
     for k in range(nb):
         assert torch.equal(codes_g[k // G, :, k % G].cpu(), want[:, k])
+
+
+@pytest.mark.parametrize("conv", ["GCN", "GAT"])
+def test_v2_device_plan_matches_torch_builder(conv):
+    """vqgnn_csr_transpose_lt (deferred count read) against the torch builder of the v2 plan."""
+    from vq_gnn_b200 import graph as G
+    dev = torch.device("cuda:0")
+    N, B = 3000, 500
+    g = H.make_graph(N, 40_000, conv, "v2", seed=13, power_law=1.5)
+    bA = H.batch_to(H.make_batch(g, B, "v2", seed=13, train=True), dev)
+    p_t = G.plan_from_v2(bA, conv, N, True, dev)
+    p_d = G.plan_from_v2_device(bA, conv, N, dev)
+    assert p_d._bwd is None                                   # nothing read back yet
+    assert torch.equal(p_t.fwd_rowptr, p_d.fwd_rowptr) and torch.equal(p_t.fwd_col, p_d.fwd_col)
+    assert torch.equal(p_t.tail_node, p_d.tail_node) and p_t.R == p_d.R
+
+    def dense_bwd(plan):
+        bdeg = (plan.bwd_rowptr[1:] - plan.bwd_rowptr[:-1]).long()
+        bj = torch.repeat_interleave(torch.arange(B, device=dev), bdeg)
+        t = torch.zeros(plan.R, B, device=dev, dtype=torch.float64)
+        return t.index_put_((plan.bwd_col.long(), bj), plan.bwd_val.double(), accumulate=True)
+    assert torch.equal(dense_bwd(p_t), dense_bwd(p_d))
+    assert torch.equal(p_t.bwd_rowptr, p_d.bwd_rowptr) and p_t.bwd_col.numel() == p_d.bwd_col.numel()

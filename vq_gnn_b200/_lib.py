@@ -46,6 +46,8 @@ _SIGNATURES = {
     "vqgnn_codes_group": (C.c_int, [vp, i32, vp, i64, i64, i32, vp, vp]),
     "vqgnn_mp_fwd_tail": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32,
                                     f32, f32, vp, i64, vp, i64, vp, vp, vp]),
+    "vqgnn_csr_transpose_workspace_bytes": (C.c_size_t, [i64]),
+    "vqgnn_csr_transpose_lt": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
     "vqgnn_plan_v1_workspace_bytes": (C.c_size_t, [i64, i64]),
     "vqgnn_plan_v1_build": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -118,7 +120,7 @@ class _Proxy:
 
 _NO_STREAM = {"vqgnn_abi_version", "vqgnn_arch_check", "vqgnn_last_error", "vqgnn_launch_count",
               "vqgnn_mp_workspace_bytes", "vqgnn_mp_num_chunks", "vqgnn_vq_assign_workspace_bytes", "vqgnn_mp_tail_group",
-              "vqgnn_plan_v1_workspace_bytes"}
+              "vqgnn_plan_v1_workspace_bytes", "vqgnn_csr_transpose_workspace_bytes"}
 
 
 def load():

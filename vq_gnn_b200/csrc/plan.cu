@@ -154,6 +154,31 @@ __global__ void plan_chunk_rows_dev_kernel(const int32_t* __restrict__ rowptr, i
   chunk_row[cI] = lo;
 }
 
+// Transposed CSR restricted to columns < B (the backward of the v2 forward: vq_gnn_v2 autograd of adj @ x, batch rows
+// only).  One warp per forward row; pass 0 counts per column, pass 1 scatters (row, value) through per-column cursors.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256)
+    plan_transpose_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                          const float* __restrict__ val, int R, int B, int* __restrict__ counters,
+                          const int32_t* __restrict__ browptr, int32_t* __restrict__ brow,
+                          float* __restrict__ bval) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 8 + warp; r < R; r += gridDim.x * 8) {
+    const int e0 = __ldg(rowptr + r), e1 = __ldg(rowptr + r + 1);
+    for (int e = e0 + lane; e < e1; e += 32) {
+      const int c = __ldg(col + e);
+      if (c < B) {
+        const int slot = atomicAdd(counters + c, 1);
+        if (SCATTER) {
+          const int d = __ldg(browptr + c) + slot;
+          brow[d] = r;
+          bval[d] = __ldg(val + e);
+        }
+      }
+    }
+  }
+}
+
 static int plan_grid(int64_t n) { return static_cast<int>(std::min<int64_t>((n + 255) / 256, 16 * kNumSMs)); }
 
 }  // namespace vqgnn
@@ -229,6 +254,32 @@ extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const flo
     VQ_LAUNCH_CHECK();
     if (int rc = vqgnn_mp_chunk_rows(i_rowptr, B, nin, chunk, i_chunk_row, stream)) return rc;
     if (int rc = vqgnn_mp_chunk_rows(b_rowptr, B, nin, chunk, b_chunk_row, stream)) return rc;
+  }
+  return VQGNN_OK;
+}
+
+extern "C" size_t vqgnn_csr_transpose_workspace_bytes(int64_t B) { return static_cast<size_t>(B) * 4 + 64; }
+
+extern "C" int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col, const float* val, int64_t R,
+                                      int64_t nnz, int64_t B, int32_t* browptr, int32_t* brow, float* bval,
+                                      int32_t* count, void* ws, void* stream) {
+  VQ_CHECK_ARG(rowptr && browptr && count && ws && R > 0 && B > 0 && B <= R && R < (1ll << 31) && nnz >= 0 &&
+                   nnz < (1ll << 31),
+               "csr_transpose_lt: bad arguments");
+  VQ_CHECK_ARG(nnz == 0 || (col && val && brow && bval), "csr_transpose_lt: null arrays");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int* cnt = static_cast<int*>(ws);
+  VQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * B, s));
+  const int grid = static_cast<int>(std::min<int64_t>((R + 7) / 8, 16 * kNumSMs));
+  if (nnz > 0) {
+    plan_transpose_kernel<false><<<grid, 256, 0, s>>>(rowptr, col, val, (int)R, (int)B, cnt, nullptr, nullptr, nullptr);
+    VQ_LAUNCH_CHECK();
+  }
+  plan_scan_kernel<<<1, 1024, 0, s>>>(cnt, (int)B, browptr, count);
+  VQ_LAUNCH_CHECK();
+  if (nnz > 0) {
+    plan_transpose_kernel<true><<<grid, 256, 0, s>>>(rowptr, col, val, (int)R, (int)B, cnt, browptr, brow, bval);
+    VQ_LAUNCH_CHECK();
   }
   return VQGNN_OK;
 }

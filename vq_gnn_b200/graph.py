@@ -97,24 +97,28 @@ class BatchPlan:
 
     def __init__(self, version: str, conv_type: str, B: int, R: int, T: int, N: int, batch_idx: Tensor,
                  fwd_rowptr: Optional[Tensor], fwd_col: Optional[Tensor], fwd_val: Optional[Tensor],
-                 fwd_rval: Optional[Tensor], tail_node: Optional[Tensor], bwd_rowptr: Tensor, bwd_col: Tensor,
-                 bwd_val: Tensor, bwd_eid: Optional[Tensor] = None, training: bool = True,
-                 extras: Optional[dict] = None, merged_builder=None, nnz: Optional[int] = None,
-                 has_rval: Optional[bool] = None):
+                 fwd_rval: Optional[Tensor], tail_node: Optional[Tensor], bwd_rowptr: Optional[Tensor],
+                 bwd_col: Optional[Tensor], bwd_val: Optional[Tensor], bwd_eid: Optional[Tensor] = None,
+                 training: bool = True, extras: Optional[dict] = None, merged_builder=None,
+                 nnz: Optional[int] = None, has_rval: Optional[bool] = None, bwd_builder=None):
         self.version, self.conv_type = version, conv_type
         self.B, self.R, self.T, self.N = B, R, T, N
         self.batch_idx = batch_idx             # int32 [B]  global node ids of the batch rows
         self._fwd = None if fwd_rowptr is None else (fwd_rowptr, fwd_col, fwd_val, fwd_rval)
         self._merged_builder = merged_builder  # () -> (rowptr int32 [R+1], col int32, val fp32, rval fp32 | None)
         self.tail_node = tail_node             # int32 [T] or None (identity)
-        self.bwd_rowptr, self.bwd_col, self.bwd_val, self.bwd_eid = bwd_rowptr, bwd_col, bwd_val, bwd_eid
+        # transposed CSR over the batch columns; may be DEFERRED (device-built v2 plans: the entry count is read back
+        # from the device only when the backward first needs it, long after the kernels that produced it finished)
+        self._bwd = None if bwd_rowptr is None else (bwd_rowptr, bwd_col, bwd_val)
+        self._bwd_builder = bwd_builder          # () -> (rowptr int32 [B+1], src row int32 [nnzT], val fp32 [nnzT])
+        self.bwd_eid = bwd_eid
         self.training = training
         self.extras = {} if extras is None else extras
         self._nnz = nnz
         self._has_rval = has_rval
         # v1: the in-batch block (forward split + transposed CSR) is small (~2 x 10^5 entries at the Reddit shape);
         # finer chunks give its kernels enough warps to fill the machine
-        self.small_chunk = small_chunk(int(bwd_col.numel())) if version == 'v1' else MP_CHUNK
+        self.small_chunk = small_chunk(int(bwd_col.numel())) if (version == 'v1' and bwd_col is not None) else MP_CHUNK
 
     def _merged(self):
         if self._fwd is None:
@@ -123,6 +127,14 @@ class BatchPlan:
             self.extras.pop('chunk_rows_fwd', None)
         return self._fwd
 
+    def _bwd_get(self):
+        if self._bwd is None:
+            self._bwd = self._bwd_builder()
+        return self._bwd
+
+    bwd_rowptr = property(lambda self: self._bwd_get()[0])  # int32 [B+1]
+    bwd_col = property(lambda self: self._bwd_get()[1])     # int32 [nnzT] source row ids (< R)
+    bwd_val = property(lambda self: self._bwd_get()[2])     # fp32  [nnzT]
     fwd_rowptr = property(lambda self: self._merged()[0])   # int32 [R+1]
     fwd_col = property(lambda self: self._merged()[1])      # int32 [nnz]: < B dense row, >= B tail entry
     fwd_val = property(lambda self: self._merged()[2])      # fp32  [nnz]
@@ -134,7 +146,7 @@ class BatchPlan:
 
     @property
     def device(self):
-        return self.bwd_rowptr.device
+        return self.batch_idx.device
 
     @property
     def nnz(self) -> int:
@@ -142,9 +154,11 @@ class BatchPlan:
 
     def tensors(self):
         """Every tensor the plan currently holds (for stream bookkeeping)."""
-        out = [self.batch_idx, self.tail_node, self.bwd_rowptr, self.bwd_col, self.bwd_val, self.bwd_eid]
+        out = [self.batch_idx, self.tail_node, self.bwd_eid]
         if self._fwd is not None:
             out += list(self._fwd)
+        if self._bwd is not None:
+            out += list(self._bwd)
 
         def rec(o):
             if isinstance(o, torch.Tensor):
@@ -183,7 +197,8 @@ class BatchPlan:
         """Build every lazily-derived piece now (on the current stream): the work partitions and, for v1
         plans with long rows, the in-batch / tail split.  `LowRankGNN.prepare` calls this so that a prefetching
         loader pays for it (and its host syncs) off the training stream."""
-        self.chunk_rows('bwd')
+        if self._bwd is not None:       # a deferred transposed CSR is finished by the first backward instead
+            self.chunk_rows('bwd')
         if (split and self.version == 'v1' and self.has_rval and self.conv_type != 'GAT'
                 and self.nnz >= TAIL_MIN_AVG_DEGREE * self.B):
             self.split_v1()
@@ -240,7 +255,7 @@ def small_chunk(nnz: int) -> int:
     return 64 if nnz < (1 << 20) else MP_CHUNK
 
 
-DEVICE_PLAN_BUILDER = True   # v1 plans on CUDA are built by csrc/plan.cu (False: the torch builder below)
+DEVICE_PLAN_BUILDER = True   # plans on CUDA are built by csrc/plan.cu (False: the torch builders below)
 import os as _os
 TAIL_CHUNK = int(_os.environ.get('VQGNN_TAIL_CHUNK', '512'))  # entries per warp task of the shared-memory tail kernel (csrc/mp_tail.cu)
 TAIL_MIN_AVG_DEGREE = 32   # below this the per-row reduce of the lane=entry kernel does not pay
@@ -280,6 +295,56 @@ def plan_from_v2(batch_A, conv_type: str, N: int, training: bool, device) -> Bat
     return BatchPlan('v2', conv_type, B, R, dim - B, N, _i32(batch_idx.to(device)),
                      _i32(rowptr), _i32(col), val.contiguous(), None, _i32(subset.to(device)[B:]),
                      bptr, bcol, bval, beid, training)
+
+
+_PINNED_COUNTS = []      # small ring of pinned int32 scalars for deferred device->host count reads
+
+
+def _pinned_count():
+    if len(_PINNED_COUNTS) < 64:
+        _PINNED_COUNTS.append(torch.empty(1, dtype=torch.int32).pin_memory())
+        return _PINNED_COUNTS[-1]
+    t = _PINNED_COUNTS.pop(0)
+    _PINNED_COUNTS.append(t)
+    return t
+
+
+def plan_from_v2_device(batch_A, conv_type: str, N: int, device) -> BatchPlan:
+    """Training-mode `plan_from_v2` with the transposed CSR built on the device (csrc/plan.cu:
+    vqgnn_csr_transpose_lt) and NO host synchronisation: the number of transposed entries is copied to pinned host
+    memory asynchronously and only read when the backward first asks for the structure."""
+    from . import _lib
+    batch_idx, subset, adj = batch_A
+    lib, st = _lib.load(), _lib.stream()
+    dev = torch.device(device)
+    rowptr, col, val = adj.csr()
+    dim = int(adj.sparse_sizes()[0])
+    B = int(batch_idx.shape[0])
+    rowptr, col = _i32(rowptr.to(dev)), _i32(col.to(dev))
+    val = val.to(dev).float().contiguous()
+    _lib.require_device(val)
+    nnz = int(col.numel())
+    browptr = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    brow = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    bval = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(lib.vqgnn_csr_transpose_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.vqgnn_csr_transpose_lt(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), dim, nnz, B,
+                                          _lib.ptr(browptr), _lib.ptr(brow), _lib.ptr(bval), _lib.ptr(count),
+                                          _lib.ptr(ws), st))
+    host_count = _pinned_count()
+    host_count.copy_(count, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+
+    def bwd():
+        ev.synchronize()
+        n = int(host_count[0])
+        return browptr, brow[:n], bval[:n]
+
+    return BatchPlan('v2', conv_type, B, dim, dim - B, N, _i32(batch_idx.to(dev)), rowptr, col, val, None,
+                     _i32(subset.to(dev)[B:]), None, None, None, None, True,
+                     extras={'_keep': (ws, count, brow, bval, browptr)}, bwd_builder=bwd)
 
 
 def _csr_ptr(rows: Tensor, n: int) -> Tensor:
@@ -431,6 +496,8 @@ def build_plan(batch_A, conv_type: str, N: int, training: bool, device) -> Batch
     if isinstance(batch_A, BatchPlan):
         return batch_A
     if len(batch_A) == 3:
+        if training and torch.device(device).type == 'cuda' and DEVICE_PLAN_BUILDER:
+            return plan_from_v2_device(batch_A, conv_type, N, device)
         return plan_from_v2(batch_A, conv_type, N, training, device)
     if len(batch_A) == 5:
         if torch.device(device).type == 'cuda' and DEVICE_PLAN_BUILDER:

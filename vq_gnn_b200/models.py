@@ -428,7 +428,7 @@ class LowRankGNN(nn.Module):
         """Build the kernel plan once per mini-batch (shared by all layers)."""
         device = device or next(self.parameters()).device
         plan = build_plan(batch_A, self.conv_type, self.num_N, self.training, device)
-        return plan.warm() if plan.bwd_col.is_cuda else plan
+        return plan.warm() if plan.device.type == 'cuda' else plan
 
     def forward(self, batch, warm_up_rate=1, unlabeled=False):
         losses_full, info_backwards_full = 0, 0
