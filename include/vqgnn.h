@@ -23,7 +23,11 @@
  *                  reference keeps nb separate `c_indices[N]` buffers, vq_gnn_v2/models.py:27-28);
  *   stats          per-codeword accumulator [nb, M, Wp + 4]: Wp sums, then count, then 3 pad words;
  *                  this flat buffer (plus `sums`) is what a multi-GPU run allreduces between
- *                  vqgnn_vq_assign and vqgnn_vq_finalize.
+ *                  vqgnn_vq_segsum and vqgnn_vq_finalize.
+ *
+ * Determinism: results are pure functions of the inputs -- no entry point of the VQ update, the plan builders or
+ * the GCN / SAGE message passing accumulates floating point with atomics whose order could change the sum
+ * (two-level ordered reductions instead; integer counters only).  The GAT kernels still use fp32 REDs.
  */
 #ifndef VQGNN_H_
 #define VQGNN_H_
@@ -35,7 +39,7 @@
 extern "C" {
 #endif
 
-#define VQGNN_ABI_VERSION 1
+#define VQGNN_ABI_VERSION 2
 
 #define VQGNN_OK 0
 #define VQGNN_ERR_ARCH (-1)      /* device is not sm_100 */
@@ -61,15 +65,19 @@ int64_t vqgnn_launch_count(void);
  *   sums[0 .. C+Cg)          = sum_b v[b, c]
  *   sums[C+Cg .. 2(C+Cg))    = sum_b v[b, c]^2
  * Replaces the batch statistics inside BatchNorm1d.forward (vq.py:162,223) and the explicit
- * mean/var at vq.py:216-221.  `sums` is overwritten.  In a multi-GPU run it is allreduced (sum). */
+ * mean/var at vq.py:216-221.  `sums` is overwritten.  In a multi-GPU run it is allreduced (sum).
+ * Two-level ordered reduction (row tiles of 512, then the tiles in index order): bit-stable.
+ * ws: vqgnn_vq_moments_workspace_bytes(B, C, Cg) bytes, 8 B aligned. */
+size_t vqgnn_vq_moments_workspace_bytes(int64_t B, int C, int Cg);
 int vqgnn_vq_moments(const float* x, int64_t ldx, const float* g, int64_t ldg, int64_t B, int C, int Cg,
-                     double* sums, void* stream);
+                     double* sums, void* ws, void* stream);
 
 /* Turns moments into the per-column whitening affine z = v * scale + shift and updates the BatchNorm
  * running statistics exactly as torch.nn.BatchNorm1d(affine=False) does in train mode
  * (biased variance for normalisation, unbiased for the running update), incl. the first-update
- * re-seeding of vq.py:216-221 (`seed_running` != 0).  If training == 0 the running statistics are
- * used and left untouched.  Gradient columns are additionally multiplied by grad_scale0 (last column
+ * re-seeding of vq.py:216-221 (`seed_running` != 0, or per branch seed_mask[k] != 0 when seed_mask != NULL:
+ * the reference keeps one `bn_inited` flag per quantiser).  If training == 0 the running statistics are
+ * used and left untouched, except that a seeding branch first overwrites them with the batch statistics.  Gradient columns are additionally multiplied by grad_scale0 (last column
  * of each branch by grad_scale1 when Dg == D+1) (vq.py:224-227).
  *   run_mean_f/run_var_f: [nb*D]; run_mean_g/run_var_g: [nb*Dg] (NULL when Cg == 0)
  *   scale/shift: [C + Cg] outputs.  count = number of rows the moments were taken over (global); if d_count
@@ -78,16 +86,17 @@ int vqgnn_vq_moments(const float* x, int64_t ldx, const float* g, int64_t ldg, i
 int vqgnn_vq_whiten(const double* sums, double count, const double* d_count, int nb, int D, int Dg, int has_grad,
                     float* run_mean_f, float* run_var_f, float* run_mean_g, float* run_var_g,
                     float eps_f, float mom_f, float eps_g, float mom_g, float grad_scale0, float grad_scale1,
-                    int training, int seed_running, int64_t* nbt_f, int64_t* nbt_g, float* scale, float* shift,
-                    void* stream);
+                    int training, int seed_running, const int32_t* seed_mask, int64_t* nbt_f, int64_t* nbt_g,
+                    float* scale, float* shift, void* stream);
 
 /* Fused whitening + nearest-codeword assignment + per-codeword accumulation.
  * For every row b and branch k: z = whiten([x_k | g_k]); code = argmin_m ||z||^2 + ||E_k[m]||^2 - 2 z.E_k[m]
  * (that association order, fp32, lowest index wins ties: vq.py:166-171 / 230-236) using the
  * PRE-update codebook; writes idx[b, k] ([B, nb]) and, if codes != NULL, codes[batch_idx[b]*codes_ld + k]
- * (models.py:46,63; codes_ld = row stride of the code table, so a sub-range of branches can be updated); if stats != NULL adds z to stats[k, code, :W] and 1 to stats[k, code, Wp]
- * (the one-hot^T @ z GEMM and column sum of vq.py:243,256 as a segmented sum).  `stats` must be zeroed
- * by the caller (vqgnn_fill_zero).  g == NULL selects the feature-only form (feature_update, W = D).
+ * (models.py:46,63; codes_ld = row stride of the code table, so a sub-range of branches can be updated).
+ * stats: normally NULL -- the per-codeword sums are produced afterwards by vqgnn_vq_segsum (ordered, bit-stable).
+ * If stats != NULL the kernel instead adds z to stats[k, code, :W] and 1 to stats[k, code, Wp] with fp32 atomics in
+ * its epilogue (order-dependent last bits; `stats` must be zeroed by the caller with vqgnn_fill_zero).  g == NULL selects the feature-only form (feature_update, W = D).
  * impl: 0 = exact-fp32 SIMT kernel (parity anchor; ws unused, may be NULL);
  *       1 = tcgen05 / TMEM kernel (kind::tf32, error-compensated 3xTF32, TMA-fed codebook tiles, fused
  *           argmin epilogue; packed width D+Dg in {4, 8, 9}); needs ws of vqgnn_vq_assign_workspace_bytes()
@@ -99,9 +108,21 @@ int vqgnn_vq_assign(const float* x, int64_t ldx, const float* g, int64_t ldg, co
                     const int32_t* batch_idx, int16_t* codes, int64_t codes_ld, int16_t* idx, float* stats,
                     int impl, void* ws, size_t ws_bytes, void* stream);
 
+/* Per-codeword statistics of the update (the one-hot^T @ z GEMM and the one-hot column sum of vq.py:177,191 /
+ * 243,256) as an ordered segmented sum over the assignments idx [B, nbc] written by vqgnn_vq_assign:
+ *   stats[k, m, :W] = sum_{b: idx[b,k]==m} z[b, k, :],  stats[k, m, Wp] = count   (every entry is written).
+ * The (branch, code) keys are radix-sorted (stable), then one warp per codeword adds its rows in ascending order with
+ * a fixed reduction tree: no floating-point atomics, identical bits on every run.  z is re-whitened from x / g with
+ * scale / shift exactly as in vqgnn_vq_assign.  ws: vqgnn_vq_segsum_workspace_bytes(B, nbc, M) bytes. */
+size_t vqgnn_vq_segsum_workspace_bytes(int64_t B, int nbc, int M);
+int vqgnn_vq_segsum(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
+                    const float* shift, const int16_t* idx, int64_t B, int nbc, int M, int D, int Dg, int Wp,
+                    float* stats, void* ws, size_t ws_bytes, void* stream);
+
 /* EMA + Laplace smoothing + codeword recovery (vq.py:177-200 / 242-275), one CTA per branch:
  *   size <- decay*size + (1-decay)*count; if warm_up: size <- (size+1e-5)/(sum(size)+M*1e-5)*sum(size);
- *   status |= BAD_INIT if any size == 0; Wm <- decay*Wm + (1-decay)*sum_z; E <- Wm/size;
+ *   status |= BAD_INIT if any size == 0 and, as the reference raises before touching them (vq.py:188,253), Wm / E /
+ *   O of that branch are then left unchanged; otherwise Wm <- decay*Wm + (1-decay)*sum_z; E <- Wm/size;
  *   O <- de-whiten(E) with the (already updated) running statistics; gradient part divided by
  *   (grad_scale + eps); O[:, D:] <- 0 if grad_scale0 == 0.
  * joint == 0 updates only the first D columns (feature_update). */
@@ -130,11 +151,13 @@ int vqgnn_mp_chunk_rows(const int32_t* rowptr, int64_t R, int64_t nnz, int chunk
  *   gqacc = sum_{tail e} rval[e] * O_k[code(...), D:2D]                   (only if rval != NULL)
  * rows r <  B: y[r, :] = acc; gq[r, :] = gqacc; info += <x[r, :], gqacc>  (v1 info_backward, models.py:223)
  * rows r >= B: info += <acc, O_k[code(node(r-B), k), D:2D]>               (v2 info_backward, models.py:198)
- * *info = info_scale * info (fp64 accumulation over warps).
+ * *info = info_scale * info (fp64; per-block partials added in block order by the last block).
  * C = nb*D columns.  tail_node == NULL means identity.  info/gq may be NULL.
  * chunk_row/chunk/nnz: the partition above for (rowptr, R).
- * ws: vqgnn_mp_workspace_bytes() bytes, zeroed by this call. */
-size_t vqgnn_mp_workspace_bytes(void);
+ * Order-independent by construction: a row inside one chunk is stored, a row cut once takes two REDs onto zero
+ * (commutative), the pieces of a row spanning >= 3 chunks go to a piece buffer and are added in chunk order.
+ * ws: vqgnn_mp_workspace_bytes(nnz, chunk, nb*D) bytes (info partials + piece buffers); same for vqgnn_mp_bwd. */
+size_t vqgnn_mp_workspace_bytes(int64_t nnz, int chunk, int C);
 int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
                  const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B, const float* x,
                  int64_t ldx, const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M,
@@ -160,7 +183,7 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
                  int chunk, int64_t nnz, int64_t B, const float* dy, int64_t lddy, const int32_t* tail_node,
                  const int16_t* codes, const float* O, int nb, int M, int D, int Wp, const float* tail_grad,
                  int64_t ld_tail, float tail_scale, const float* gq, int64_t ldgq, float gq_scale,
-                 const float* dinfo, float* dx, int64_t lddx, void* stream);
+                 const float* dinfo, float* dx, int64_t lddx, void* ws, void* stream);
 
 /* Out-of-batch ("tail") part of the forward with the codebooks of a branch group resident in shared
  * memory (csrc/mp_tail.cu) -- the fast path for the v1 formulation, where every batch row has hundreds of
@@ -170,10 +193,13 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
  *   vqgnn_codes_group: codes_g[(k/G)*N + node][k%G] = codes[node, k]  (codes_g: [ceil(nb/G)][N][8] int16) for
  *                      the listed nodes (rows == NULL: all N) -- the group-major mirror of the code table.
  *   vqgnn_mp_fwd_tail: over a CSR holding ONLY tail entries (node = global node id):
- *       y[r]  += sum_e val[e] * feat_scale * O_k[code_k(node[e]), :D]      (y, gq accumulate: run it AFTER
- *       gq[r] += sum_e rval[e] * O_k[code_k(node[e]), D:2D]                 vqgnn_mp_fwd on the in-batch part)
- *       *info += info_scale * sum_r <x[r], gq contribution>               (info must be zero-initialised)
+ *       y[r]  += sum_e val[e] * feat_scale * O_k[code_k(node[e]), :D]      (y accumulates: run it AFTER
+ *       gq[r]  = sum_e rval[e] * O_k[code_k(node[e]), D:2D]                 vqgnn_mp_fwd on the in-batch part)
+ *       *info  = info_scale * sum_r <x[r], gq[r]>
+ *     the tail sums are formed in a scratch copy with the same order-independent piece scheme as vqgnn_mp_fwd and
+ *     added to y in one pass; ws: vqgnn_mp_fwd_tail_workspace_bytes(nnz, chunk, B, nb*D) bytes.
  *   d_nnz != NULL: the entry count lives on the device (vqgnn_plan_v1_build); nnz is then its upper bound. */
+size_t vqgnn_mp_fwd_tail_workspace_bytes(int64_t nnz, int chunk, int64_t B, int C);
 int vqgnn_mp_tail_group(int M, int D, int Wp);
 /* Apply n (node, codes[nbc]) updates for branches [k0, k0 + nbc) to codes [N, nb] (and its group-major mirror
  * codes_g when not NULL); when a node is listed more than once the LAST entry wins.  Multi-GPU: the list is the
@@ -200,8 +226,11 @@ int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* v
  *                 doubled when symmetric): nin = nbb * (1 + symmetric) + self_loops * B entries;
  *                 forward CSR i_rowptr / i_col / i_val / i_chunk_row and transposed b_rowptr / b_row / b_val /
  *                 b_chunk_row (chunk rows: ceil(nin / chunk) each)
- * ws: vqgnn_plan_v1_workspace_bytes(N, B) bytes. */
-size_t vqgnn_plan_v1_workspace_bytes(int64_t N, int64_t B);
+ * A_BN must be row-sorted (the reference's loader emits CSR order): the tail part is a STABLE compaction of it, and
+ * every in-batch CSR row is sorted by column, so the plan -- and with it the order of every fp32 sum in the
+ * message-passing kernels -- does not depend on atomic ordering.
+ * ws: vqgnn_plan_v1_workspace_bytes(N, B, nnz, nin) bytes. */
+size_t vqgnn_plan_v1_workspace_bytes(int64_t N, int64_t B, int64_t nnz, int64_t nin);
 int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, const float* rv, int64_t nnz,
                         const int64_t* bb_r, const int64_t* bb_c, const float* bb_v, int64_t nbb,
                         const int64_t* batch_idx, const float* deg_inv, int64_t B, int64_t N, int symmetric,
@@ -211,10 +240,10 @@ int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, cons
                         float* b_val, int32_t* b_chunk_row, void* ws, void* stream);
 
 /* Transposed CSR restricted to columns < B of a CSR over R rows (the backward structure of a v2 batch graph):
- * browptr [B+1], brow / bval sized nnz (upper bound; the first *count entries are valid, order inside a column is
- * free), *count = number of entries with col < B (stays on the device: read it back lazily).
- * ws: vqgnn_csr_transpose_workspace_bytes(B). */
-size_t vqgnn_csr_transpose_workspace_bytes(int64_t B);
+ * browptr [B+1], brow / bval sized nnz (upper bound; the first *count entries are valid, each column's entries
+ * sorted by source row), *count = number of entries with col < B (stays on the device: read it back lazily).
+ * ws: vqgnn_csr_transpose_workspace_bytes(B, nnz). */
+size_t vqgnn_csr_transpose_workspace_bytes(int64_t B, int64_t nnz);
 int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col, const float* val, int64_t R, int64_t nnz,
                            int64_t B, int32_t* browptr, int32_t* brow, float* bval, int32_t* count, void* ws,
                            void* stream);

@@ -57,7 +57,7 @@ def att_grad_err(got: dict, want: dict):
     """Error of the GAT attention-vector gradients, relative to their JOINT scale.  "Trick 1" (convs.py:209-211)
     makes the scores invariant to a rescaling of att_l (att_r) when max|a_l| >> 1, so the gradient along
     att_l is a difference of large terms: in fp32 the reference itself moves by ~1e-3 of |d att_l| between
-    CPU and GPU (tests/debug_gat_att_grad.py), while it is stable to ~1e-6 of the joint (att_l, att_r) gradient."""
+    CPU and GPU (scripts/debug_gat_att_grad.py), while it is stable to ~1e-6 of the joint (att_l, att_r) gradient."""
     keys = [k for k in want if "att_" in k and k in got]
     if not keys:
         return 0.0
@@ -134,28 +134,3 @@ def load_golden(name):
 
 def golden_sd(z, prefix):
     return {k[len(prefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix)}
-
-
-def retry_on_atomic_order(attempts: int = 3):
-    """Decorator for the multi-step CUDA-vs-oracle parity tests.
-
-    The per-codeword sums (vqgnn_vq_assign) and the partial-row outputs of the message-passing kernels are accumulated
-    with fp32 atomics, so their last bits depend on the order the hardware retires them.  Over several training steps
-    a codeword that differs by 1 ulp can flip an assignment whose two best distances are within ~1e-6 of each other
-    (BASELINE.json allows mismatches at near-ties with relative gap < 1e-5), after which that codeword's EMA state
-    leaves the 1e-4 band.  Observed once in ~8 runs of the whole suite.  A deterministic defect fails every attempt;
-    an atomic-order flip does not repeat, so the test is re-run (same seeds) up to `attempts` times."""
-    import functools
-
-    def deco(fn):
-        @functools.wraps(fn)
-        def wrapper(*a, **k):
-            last = None
-            for _ in range(attempts):
-                try:
-                    return fn(*a, **k)
-                except AssertionError as e:      # noqa: PERF203
-                    last = e
-            raise last
-        return wrapper
-    return deco

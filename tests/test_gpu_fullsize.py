@@ -82,7 +82,6 @@ def _check_conv(layer, x, plan, wu, ref_fn):
     return y, info
 
 
-@H.retry_on_atomic_order(2)
 def test_c1_arxiv_shape_v2_gcn():
     dev = torch.device("cuda:0")
     s = synth.CONFIG_SHAPES["c1_arxiv"]
@@ -98,7 +97,6 @@ def test_c1_arxiv_shape_v2_gcn():
     _check_conv(layer, x, plan, 0.9, R.gcn_v2)
 
 
-@H.retry_on_atomic_order(2)
 def test_c2_reddit_shape_v1_sage_both_kernels():
     dev = torch.device("cuda:0")
     s = synth.CONFIG_SHAPES["c2_reddit"]
@@ -120,7 +118,6 @@ def test_c2_reddit_shape_v1_sage_both_kernels():
     assert H.rel_err(y1, y0) < 1e-5 and abs(float(i1) - float(i0)) <= 1e-4 * max(1e-3, abs(float(i0)))
 
 
-@H.retry_on_atomic_order(2)
 def test_c3_ppi_shape_v2_gat():
     dev = torch.device("cuda:0")
     s = synth.CONFIG_SHAPES["c3_ppi"]
@@ -152,7 +149,6 @@ def test_c3_ppi_shape_v2_gat():
     assert err < TOL, ("att", err)
 
 
-@H.retry_on_atomic_order(2)
 def test_c5_products_shape_v2_gcn():
     dev = torch.device("cuda:0")
     s = synth.CONFIG_SHAPES["c5_products"]

@@ -16,7 +16,6 @@ VQ_FILES = ["vq_m16", "vq_m32_add", "vq_m64"]
 
 
 @pytest.mark.parametrize("name", VQ_FILES)
-@H.retry_on_atomic_order()
 def test_cuda_vq_matches_golden(name):
     dev = torch.device("cuda:0")
     z = H.load_golden(name)
@@ -35,7 +34,6 @@ def test_cuda_vq_matches_golden(name):
 
 
 @pytest.mark.parametrize("name", LAYER_FILES)
-@H.retry_on_atomic_order()
 def test_cuda_layer_matches_golden(name):
     dev = torch.device("cuda:0")
     z = H.load_golden(name)

@@ -19,10 +19,14 @@ def _pin(t):
     return t.contiguous().pin_memory()
 
 
-@pytest.mark.parametrize("version,conv,threaded", [("v1", "SAGE", False), ("v1", "GCN", True), ("v2", "GCN", False),
-                                                   ("v2", "GAT", True)])
-@H.retry_on_atomic_order()
+@pytest.mark.parametrize("version,conv,threaded", [("v1", "SAGE", False), ("v1", "SAGE", True), ("v1", "GCN", True),
+                                                   ("v2", "GCN", False), ("v2", "GCN", True), ("v2", "SAGE", True),
+                                                   ("v2", "GAT", False), ("v2", "GAT", True)])
 def test_prefetched_batches_train_like_direct_ones(version, conv, threaded):
+    """GCN / SAGE: the whole path (plan builders, message passing, VQ update) is free of order-dependent float
+    accumulation, so a run fed through the prefetcher (side stream, optionally a worker thread) must reproduce the
+    direct run BIT FOR BIT -- any race or atomic-order dependence shows up as a differing bit.  GAT (fp32 REDs in
+    its kernels): same losses / state within 1e-4 on the scale of each tensor."""
     dev = torch.device("cuda:0")
     N, B, M, C = 600, 120, 16, 8
     g = H.make_graph(N, 6000, conv, version, seed=3)
@@ -38,7 +42,7 @@ def test_prefetched_batches_train_like_direct_ones(version, conv, threaded):
         m = V.LowRankGNN(C, 8, 5, 2, 0., M, 4, N, no_second_fc=True, skip=False, commitment_cost=0.,
                          grad_scale=[1, 1], act='relu', bn_flag=True, warm_up_flag=True, conv_type=conv,
                          version=version).to(dev).train()
-        return m, torch.optim.SGD(m.parameters(), lr=1e-2)
+        return m, torch.optim.SGD(m.parameters(), lr=1e-3)
 
     def step(m, opt, x, bA, y, i):
         if i == 1:
@@ -59,6 +63,13 @@ def test_prefetched_batches_train_like_direct_ones(version, conv, threaded):
         x, plan, y = pf.next()
         got.append(step(m1, o1, x, plan, y, i))
     pf.drain()
-    assert ref == pytest.approx(got, rel=1e-4, abs=1e-5)     # two CUDA runs: fp32 atomics reorder the sums
-    for (k, a), (_, b) in zip(m0.state_dict().items(), m1.state_dict().items()):
-        assert torch.allclose(a.float(), b.float(), rtol=1e-4, atol=1e-6), k
+    sd0, sd1 = m0.state_dict(), m1.state_dict()
+    if conv != "GAT":
+        assert ref == got, (ref, got)
+        for k in sd0:
+            assert torch.equal(sd0[k], sd1[k]), k
+    else:
+        assert ref == pytest.approx(got, rel=1e-4, abs=1e-5)
+        for k in sd0:
+            a, b = sd0[k].float(), sd1[k].float()
+            assert float((a - b).abs().max()) <= 1e-4 * max(float(a.abs().max()), 1e-6), k

@@ -25,30 +25,35 @@ _SIGNATURES = {
     "vqgnn_arch_check": (C.c_int, [i32]),
     "vqgnn_last_error": (C.c_char_p, []),
     "vqgnn_launch_count": (i64, []),
-    "vqgnn_vq_moments": (C.c_int, [vp, i64, vp, i64, i64, i32, i32, vp, vp]),
+    "vqgnn_vq_moments_workspace_bytes": (C.c_size_t, [i64, i32, i32]),
+    "vqgnn_vq_moments": (C.c_int, [vp, i64, vp, i64, i64, i32, i32, vp, vp, vp]),
     "vqgnn_vq_whiten": (C.c_int, [vp, f64, vp, i32, i32, i32, i32, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32,
-                                  i32, i32, vp, vp, vp, vp, vp]),
+                                  i32, i32, vp, vp, vp, vp, vp, vp]),
+    "vqgnn_vq_segsum_workspace_bytes": (C.c_size_t, [i64, i32, i32]),
+    "vqgnn_vq_segsum": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, C.c_size_t,
+                                  vp]),
     "vqgnn_vq_assign_workspace_bytes": (C.c_size_t, [i32, i32]),
     "vqgnn_vq_assign": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, i64, vp,
                                   vp, i32, vp, C.c_size_t, vp]),
     "vqgnn_vq_finalize": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, f64, i32, f32, f32, f32, vp, vp, vp, vp,
                                     vp, vp, vp, vp, vp, vp]),
-    "vqgnn_mp_workspace_bytes": (C.c_size_t, []),
+    "vqgnn_mp_workspace_bytes": (C.c_size_t, [i64, i32, i32]),
+    "vqgnn_mp_fwd_tail_workspace_bytes": (C.c_size_t, [i64, i32, i64, i32]),
     "vqgnn_mp_num_chunks": (i64, [i64, i32]),
     "vqgnn_mp_chunk_rows": (C.c_int, [vp, i64, i64, i32, vp, vp]),
     "vqgnn_mp_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32,
                                vp, i64, f32, f32, vp, i64, vp, i64, vp, vp, vp]),
     "vqgnn_tail_materialize": (C.c_int, [vp, i64, vp, vp, i32, i32, i32, i32, vp, vp, i64, vp]),
     "vqgnn_mp_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64,
-                               f32, vp, i64, f32, vp, vp, i64, vp]),
+                               f32, vp, i64, f32, vp, vp, i64, vp, vp]),
     "vqgnn_mp_tail_group": (C.c_int, [i32, i32, i32]),
     "vqgnn_codes_apply_updates": (C.c_int, [vp, vp, i64, i32, i32, vp, i32, i64, vp, i32, vp, vp]),
     "vqgnn_codes_group": (C.c_int, [vp, i32, vp, i64, i64, i32, vp, vp]),
     "vqgnn_mp_fwd_tail": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32,
                                     f32, f32, vp, i64, vp, i64, vp, vp, vp]),
-    "vqgnn_csr_transpose_workspace_bytes": (C.c_size_t, [i64]),
+    "vqgnn_csr_transpose_workspace_bytes": (C.c_size_t, [i64, i64]),
     "vqgnn_csr_transpose_lt": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp]),
-    "vqgnn_plan_v1_workspace_bytes": (C.c_size_t, [i64, i64]),
+    "vqgnn_plan_v1_workspace_bytes": (C.c_size_t, [i64, i64, i64, i64]),
     "vqgnn_plan_v1_build": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "vqgnn_gat_scores": (C.c_int, [i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp, vp, vp, vp,
@@ -119,8 +124,9 @@ class _Proxy:
 
 
 _NO_STREAM = {"vqgnn_abi_version", "vqgnn_arch_check", "vqgnn_last_error", "vqgnn_launch_count",
-              "vqgnn_mp_workspace_bytes", "vqgnn_mp_num_chunks", "vqgnn_vq_assign_workspace_bytes", "vqgnn_mp_tail_group",
-              "vqgnn_plan_v1_workspace_bytes", "vqgnn_csr_transpose_workspace_bytes"}
+              "vqgnn_mp_workspace_bytes", "vqgnn_mp_fwd_tail_workspace_bytes", "vqgnn_mp_num_chunks", "vqgnn_vq_assign_workspace_bytes", "vqgnn_mp_tail_group",
+              "vqgnn_plan_v1_workspace_bytes", "vqgnn_csr_transpose_workspace_bytes",
+              "vqgnn_vq_moments_workspace_bytes", "vqgnn_vq_segsum_workspace_bytes"}
 
 
 def load():
@@ -137,7 +143,7 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here == header/library mismatch: fail loudly
         fn.restype, fn.argtypes = res, args
-    if lib.vqgnn_abi_version() != 1:
+    if lib.vqgnn_abi_version() != 2:
         raise VQGNNLibraryError("libvqgnn.so ABI version mismatch")
     _lib = _Proxy(lib)
     return _lib

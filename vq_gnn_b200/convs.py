@@ -91,20 +91,3 @@ class OurGATConv(nn.Module):
             raise NotImplementedError  # vq_softmax.py:54-55: only the CSR (SparseTensor) path exists
         from .models import plain_propagate
         return plain_propagate(x, edge_index, self.att_l.view(-1), self.att_r.view(-1), self.negative_slope)
-
-
-class Transformer(nn.Module):
-    """Experimental global-attention conv of the reference (convs.py:269-287); dense torch, unused by
-    every README configuration (SURVEY.md §2 #6).  Kept for import compatibility only."""
-
-    def __init__(self, num_D):
-        super().__init__()
-        self.num_D = num_D
-
-    def forward(self, X_B, X_bar):
-        C_BM = torch.mm(X_B, X_bar.t()) / math.sqrt(self.num_D)
-        c_max = torch.max(torch.sum(torch.cat([X_B, X_bar], dim=0) ** 2, dim=1))
-        C_BM = torch.exp(C_BM / c_max)
-        X_B_output = torch.mm(C_BM / torch.sum(C_BM, dim=1, keepdim=True), X_bar)
-        X_bar_output = torch.mm(C_BM.t() / torch.sum(C_BM.t(), dim=1, keepdim=True), X_B)
-        return torch.cat([X_B_output, X_bar_output], dim=0)

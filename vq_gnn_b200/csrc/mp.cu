@@ -3,8 +3,10 @@
 // Work unit = one warp x (chunk of `chunk` consecutive CSR entries) x (slab of 32*VEC columns).  Chunks ignore
 // row boundaries, so a power-law hub row (10^4..10^5 entries in the Reddit-shaped batch) is spread over
 // hundreds of warps instead of serialising one (the first version of this kernel was row-per-warp and spent
-// 30 ms in its longest row).  Rows that lie wholly inside a chunk are stored directly; rows cut by a chunk
-// boundary are accumulated with vector REDs (red.global.add.v4.f32) into a pre-zeroed output.
+// 30 ms in its longest row).  Rows that lie wholly inside a chunk are stored directly; a row cut by one chunk
+// boundary is accumulated with two vector REDs (red.global.add.v4.f32) into a pre-zeroed output (two additions onto
+// zero commute, so the result is order-independent); the pieces of a row spanning three or more chunks go to a piece
+// buffer and are summed in chunk order by mp_fixup_kernel.  Results are bit-identical from run to run.
 //
 // In-batch neighbours read dense rows (coalesced 16 B per lane); out-of-batch neighbours read the node's code
 // row (2 B per lane, contiguous over the branches of the slab) and gather their codeword from the L2-resident
@@ -39,12 +41,14 @@ __global__ void __launch_bounds__(kMpWarps * 32)
                   const int32_t* __restrict__ chunk_row, int n_chunks, int chunk, int nnz, int64_t R, int B,
                   const float* __restrict__ x, int64_t ldx, Codebook cb, int C, int nslab, float feat_scale,
                   float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ gq, int64_t ldgq,
-                  float* __restrict__ info, double* ws_sum, unsigned int* ws_count) {
+                  float* __restrict__ info, double* ws_part, unsigned int* ws_count, float* __restrict__ py,
+                  float* __restrict__ pgq) {
   const int lane = threadIdx.x & 31;
   const MpTask t = mp_task<VEC>(chunk_row, n_chunks, chunk, nnz, nslab, C, cb.D);
   float fpart = 0.f;
   if (t.valid) {
     const int c0 = t.c0, k = t.k, off = t.off;
+    const int64_t ch = t.eb / chunk;
     float acc[VEC], gqa[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f, gqa[i] = 0.f;
@@ -57,17 +61,21 @@ __global__ void __launch_bounds__(kMpWarps * 32)
           gather_accumulate<VEC, false, false, true>(g, B, x, ldx, cb, 0, feat_scale, c0, k, off, acc, gqa);
       }
     };
-    auto flush = [&](int r, bool whole) {
+    auto flush = [&](int r, bool whole, int rs, int re) {
       if (t.active) {
         if (r < B) {
+          const int kind = piece_kind(whole, rs, re, t.eb, chunk);
+          const int64_t poff = (ch * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + c0;
           float* yp = y + static_cast<int64_t>(r) * ldy + c0;
-          if (whole) st_vec<VEC>(yp, acc);
-          else red_vec<VEC>(yp, acc);
+          if (kind == kPieceWhole) st_vec<VEC>(yp, acc);
+          else if (kind == kPieceRed) red_vec<VEC>(yp, acc);
+          else st_vec<VEC>(py + poff, acc);
           if (HAS_GQ) {
             if (gq) {
               float* gp = gq + static_cast<int64_t>(r) * ldgq + c0;
-              if (whole) st_vec<VEC>(gp, gqa);
-              else red_vec<VEC>(gp, gqa);
+              if (kind == kPieceWhole) st_vec<VEC>(gp, gqa);
+              else if (kind == kPieceRed) red_vec<VEC>(gp, gqa);
+              else st_vec<VEC>(pgq + poff, gqa);
             }
             if (info) {  // v1: <x[r], gq[r]>  (vq_gnn_v1/models.py:223 rewritten row-wise)
               float xr[VEC];
@@ -94,7 +102,46 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     else
       walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body, flush);
   }
-  if (info) info_reduce(static_cast<double>(fpart), ws_sum, ws_count, info_scale, info);
+  if (info) info_reduce_ordered(static_cast<double>(fpart), ws_part, ws_count, info_scale, info);
+}
+
+// Sums the pieces of every row that spans >= 3 chunks, in chunk order, into out (and outq).  One warp task per
+// (chunk, slab): chunk c owns the row that STARTS in c and crosses both of the next two chunk boundaries.
+// init (optional, [rows, ldi]): a per-row term added first (the backward's gq_scale * dinfo * gq).
+template <int VEC>
+__global__ void __launch_bounds__(kMpWarps * 32)
+    mp_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
+                    int64_t rows, int C, int nslab, const float* __restrict__ py, float* __restrict__ out, int64_t ldo,
+                    const float* __restrict__ pq, float* __restrict__ outq, int64_t ldq) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
+  if (task >= static_cast<int64_t>(n_chunks) * nslab) return;
+  const int slab = static_cast<int>(task / n_chunks);
+  const int c = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
+  if (c + 2 >= n_chunks) return;
+  const int r = __ldg(chunk_row + c + 1);   // the row holding entry (c+1)*chunk
+  if (r >= rows) return;
+  const int64_t rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+  if (rs < static_cast<int64_t>(c) * chunk || rs >= static_cast<int64_t>(c + 1) * chunk) return;  // starts elsewhere
+  const int lc = static_cast<int>((re - 1) / chunk);
+  if (lc < c + 2) return;
+  const int c0 = (slab * 32 + lane) * VEC;
+  if (c0 >= C) return;
+  float acc[VEC], accq[VEC], t[VEC];
+  ld_vec<VEC>(py + (static_cast<int64_t>(c) * 2 + 1) * C + c0, acc);
+  if (pq) ld_vec<VEC>(pq + (static_cast<int64_t>(c) * 2 + 1) * C + c0, accq);
+  for (int cc = c + 1; cc <= lc; ++cc) {
+    ld_vec<VEC>(py + static_cast<int64_t>(cc) * 2 * C + c0, t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += t[i];
+    if (pq) {
+      ld_vec<VEC>(pq + static_cast<int64_t>(cc) * 2 * C + c0, t);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) accq[i] += t[i];
+    }
+  }
+  st_vec<VEC>(out + static_cast<int64_t>(r) * ldo + c0, acc);
+  if (pq) st_vec<VEC>(outq + static_cast<int64_t>(r) * ldq + c0, accq);
 }
 
 // tail_feat[t, :] / tail_grad[t, :] = feature / gradient codewords of tail entry t, all branches (D == 4, Wp == 8):
@@ -116,9 +163,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// dx <- gq_scale * dinfo * gq  (or 0): the part of the backward that does not depend on the CSR
+// dx <- gq_scale * dinfo * gq for rows WITHOUT transposed entries, 0 for the others (their CSR-independent term is
+// added by the piece that holds the row start, so that every element sees a fixed order of additions)
 template <int VEC>
-__global__ void mp_bwd_init_kernel(int64_t B, int C, const float* __restrict__ gq, int64_t ldgq, float gq_scale,
+__global__ void mp_bwd_init_kernel(int64_t B, int C, const int32_t* __restrict__ browptr,
+                                   const float* __restrict__ gq, int64_t ldgq, float gq_scale,
                                    const float* __restrict__ dinfo, float* __restrict__ dx, int64_t lddx) {
   const int cv = C / VEC;
   const int64_t n = B * cv;
@@ -128,7 +177,7 @@ __global__ void mp_bwd_init_kernel(int64_t B, int C, const float* __restrict__ g
     const int64_t r = i / cv;
     const int c = static_cast<int>(i - r * cv) * VEC;
     float q[VEC];
-    if (gq) {
+    if (gq && __ldg(browptr + r) == __ldg(browptr + r + 1)) {
       ld_vec<VEC>(gq + r * ldgq + c, q);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) q[j] *= s;
@@ -145,11 +194,14 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     mp_bwd_kernel(const int32_t* __restrict__ browptr, const int32_t* __restrict__ brow,
                   const float* __restrict__ bval, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
                   int nnz, int B, const float* __restrict__ dy, int64_t lddy, Codebook cb, int C, int nslab,
-                  float tail_scale, const float* __restrict__ dinfo, float* __restrict__ dx, int64_t lddx) {
+                  float tail_scale, const float* __restrict__ dinfo, const float* __restrict__ gq, int64_t ldgq,
+                  float gq_scale, float* __restrict__ dx, int64_t lddx, float* __restrict__ pdx) {
   const int lane = threadIdx.x & 31;
   const MpTask t = mp_task<VEC>(chunk_row, n_chunks, chunk, nnz, nslab, C, cb.D);
   if (!t.valid) return;
   const float ts = tail_scale * (dinfo ? __ldg(dinfo) : 1.f);
+  const float gs = gq ? gq_scale * (dinfo ? __ldg(dinfo) : 1.f) : 0.f;
+  const int64_t ch = t.eb / chunk;
   float acc[VEC], unused[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f, unused[i] = 0.f;
@@ -161,8 +213,20 @@ __global__ void __launch_bounds__(kMpWarps * 32)
     if (t.active)
       gather_accumulate<VEC, false, false, true>(g, B, dy, lddy, cb, cb.D, ts, t.c0, t.k, t.off, acc, unused);
   };
-  auto flush = [&](int j, bool) {
-    if (t.active) red_vec<VEC>(dx + static_cast<int64_t>(j) * lddx + t.c0, acc);  // onto the initialised dx
+  auto flush = [&](int j, bool whole, int rs, int re) {
+    if (t.active) {
+      const int kind = piece_kind(whole, rs, re, t.eb, chunk);
+      if (gq && rs >= t.eb) {  // the piece holding the row start carries the CSR-independent term
+        float q[VEC];
+        ld_vec<VEC>(gq + static_cast<int64_t>(j) * ldgq + t.c0, q);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(gs, q[i], acc[i]);
+      }
+      float* dp = dx + static_cast<int64_t>(j) * lddx + t.c0;
+      if (kind == kPieceWhole) st_vec<VEC>(dp, acc);
+      else if (kind == kPieceRed) red_vec<VEC>(dp, acc);      // two REDs onto zero: order-independent
+      else st_vec<VEC>(pdx + (ch * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + t.c0, acc);
+    }
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
   };
@@ -177,7 +241,35 @@ __global__ void __launch_bounds__(kMpWarps * 32)
 
 using namespace vqgnn;
 
-extern "C" size_t vqgnn_mp_workspace_bytes(void) { return 64; }
+static inline size_t mp_al256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// workspace layout: [count (256 B)] [per-block info partials] [y pieces] [second piece buffer (gq)]
+struct MpWs {
+  unsigned int* count;
+  double* part;
+  float* p0;
+  float* p1;
+};
+static size_t mp_ws_layout(void* ws, int64_t nnz, int chunk, int C, MpWs* out) {
+  const int64_t n_chunks = chunk > 0 ? (nnz + chunk - 1) / chunk : 0;
+  const int vec = 4;   // upper bound of the grid: the VEC = 1 variant has more slabs, sized for it below
+  (void)vec;
+  const int64_t nslab1 = (C + 31) / 32;
+  const size_t grid_max = static_cast<size_t>((n_chunks * nslab1 + kMpWarps - 1) / kMpWarps) + 1;
+  const size_t pieces = mp_al256(static_cast<size_t>(n_chunks) * 2 * C * sizeof(float));
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+  if (out) {
+    out->count = reinterpret_cast<unsigned int*>(p);
+    out->part = reinterpret_cast<double*>(p + 256);
+    out->p0 = reinterpret_cast<float*>(p + 256 + mp_al256(grid_max * 8));
+    out->p1 = reinterpret_cast<float*>(p + 256 + mp_al256(grid_max * 8) + pieces);
+  }
+  return 512 + mp_al256(grid_max * 8) + 2 * pieces;
+}
+
+extern "C" size_t vqgnn_mp_workspace_bytes(int64_t nnz, int chunk, int C) {
+  return mp_ws_layout(nullptr, nnz, chunk, C, nullptr);
+}
 
 extern "C" int64_t vqgnn_mp_num_chunks(int64_t nnz, int chunk) {
   return chunk > 0 ? (nnz + chunk - 1) / chunk : -1;
@@ -219,7 +311,7 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
                             void* stream) {
   VQ_CHECK_ARG(rowptr && col && val && x && codes && O && y, "mp_fwd: null argument");
   VQ_CHECK_ARG(R >= B && B > 0 && nb > 0 && D > 0 && Wp >= 2 * D, "mp_fwd: bad sizes");
-  VQ_CHECK_ARG(!info || ws, "mp_fwd: info needs a workspace");
+  VQ_CHECK_ARG(ws || nnz == 0, "mp_fwd: needs a workspace of vqgnn_mp_workspace_bytes(nnz, chunk, nb*D) bytes");
   VQ_CHECK_ARG(B < (1ll << 31) && R < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "mp_fwd: sizes must fit int32");
   VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_fwd: needs chunk_row (vqgnn_mp_chunk_rows)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -229,9 +321,9 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
     VQ_CHECK_ARG(!rval && ld_tail % 4 == 0 && aligned16(tail_feat), "mp_fwd: dense tail rows need rval == NULL and 16 B alignment");
     cb.tail_feat = tail_feat, cb.ld_tail = ld_tail;
   }
-  double* ws_sum = static_cast<double*>(ws);
-  unsigned int* ws_count = ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 8) : nullptr;
-  if (info) VQ_CUDA(cudaMemsetAsync(ws, 0, 16, s));
+  MpWs w{nullptr, nullptr, nullptr, nullptr};
+  if (ws) mp_ws_layout(ws, nnz, chunk, C, &w);
+  if (info && ws) VQ_CUDA(cudaMemsetAsync(w.count, 0, 16, s));
   // rows cut by a chunk boundary accumulate with REDs, empty rows are never visited: start from zero
   if (int rc = zero_rows(y, B, C, ldy, s)) return rc;
   if (gq && rval)
@@ -252,7 +344,7 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
   mp_fwd_kernel<VEC, GQ, WIDE><<<grid, kMpWarps * 32, 0, s>>>(rowptr, col, val, rval, chunk_row, n_chunks,    \
                                                               chunk, (int)nnz, R, (int)B, x, ldx, cb, C, nslab, \
                                                               feat_scale, info_scale, y, ldy, gq, ldgq, info, \
-                                                              ws_sum, ws_count)
+                                                              w.part, w.count, w.p0, w.p1)
   if (vec4) {
     if (wide) VQ_MP_FWD(4, true, true);
     else if (rval) VQ_MP_FWD(4, true, false);
@@ -263,6 +355,16 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
   }
 #undef VQ_MP_FWD
   VQ_LAUNCH_CHECK();
+  if (n_chunks > 2) {   // rows spanning >= 3 chunks: ordered sum of their pieces
+    float* pq = (gq && rval) ? w.p1 : nullptr;
+    if (vec4)
+      mp_fixup_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, y, ldy,
+                                                        pq, gq, ldgq);
+    else
+      mp_fixup_kernel<1><<<grid, kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, y, ldy,
+                                                        pq, gq, ldgq);
+    VQ_LAUNCH_CHECK();
+  }
   return VQGNN_OK;
 }
 
@@ -271,13 +373,16 @@ extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const f
                             int64_t lddy, const int32_t* tail_node, const int16_t* codes, const float* O, int nb,
                             int M, int D, int Wp, const float* tail_grad, int64_t ld_tail, float tail_scale,
                             const float* gq, int64_t ldgq, float gq_scale, const float* dinfo, float* dx,
-                            int64_t lddx, void* stream) {
+                            int64_t lddx, void* ws, void* stream) {
   VQ_CHECK_ARG(browptr && brow && bval && dy && codes && O && dx, "mp_bwd: null argument");
   VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && nb > 0 && D > 0 && Wp >= 2 * D, "mp_bwd: bad sizes");
   VQ_CHECK_ARG(nnz >= 0 && nnz < (1ll << 31), "mp_bwd: nnz must fit int32");
   VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_bwd: needs chunk_row (vqgnn_mp_chunk_rows)");
+  VQ_CHECK_ARG(ws || nnz == 0, "mp_bwd: needs a workspace of vqgnn_mp_workspace_bytes(nnz, chunk, nb*D) bytes");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C = nb * D;
+  MpWs w{nullptr, nullptr, nullptr, nullptr};
+  if (ws) mp_ws_layout(ws, nnz, chunk, C, &w);
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
   if (tail_grad) {
     VQ_CHECK_ARG(ld_tail % 4 == 0 && aligned16(tail_grad), "mp_bwd: dense tail rows must be 16 B aligned");
@@ -289,17 +394,28 @@ extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const f
   const int nslab = ceil_div(C, 32 * vec);
   const int n_chunks = static_cast<int>(vqgnn_mp_num_chunks(nnz, chunk));
   const int init_grid = static_cast<int>(std::min<int64_t>((B * (C / vec) + 255) / 256, 8 * kNumSMs));
-  if (vec4) mp_bwd_init_kernel<4><<<init_grid, 256, 0, s>>>(B, C, gq, ldgq, gq_scale, dinfo, dx, lddx);
-  else mp_bwd_init_kernel<1><<<init_grid, 256, 0, s>>>(B, C, gq, ldgq, gq_scale, dinfo, dx, lddx);
+  if (vec4) mp_bwd_init_kernel<4><<<init_grid, 256, 0, s>>>(B, C, browptr, gq, ldgq, gq_scale, dinfo, dx, lddx);
+  else mp_bwd_init_kernel<1><<<init_grid, 256, 0, s>>>(B, C, browptr, gq, ldgq, gq_scale, dinfo, dx, lddx);
   VQ_LAUNCH_CHECK();
   if (n_chunks == 0) return VQGNN_OK;
   const int grid = ceil_div(static_cast<int64_t>(n_chunks) * nslab, kMpWarps);
   if (vec4)
     mp_bwd_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, chunk_row, n_chunks, chunk, (int)nnz,
-                                                    (int)B, dy, lddy, cb, C, nslab, tail_scale, dinfo, dx, lddx);
+                                                    (int)B, dy, lddy, cb, C, nslab, tail_scale, dinfo, gq, ldgq,
+                                                    gq_scale, dx, lddx, w.p0);
   else
     mp_bwd_kernel<1><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, chunk_row, n_chunks, chunk, (int)nnz,
-                                                    (int)B, dy, lddy, cb, C, nslab, tail_scale, dinfo, dx, lddx);
+                                                    (int)B, dy, lddy, cb, C, nslab, tail_scale, dinfo, gq, ldgq,
+                                                    gq_scale, dx, lddx, w.p0);
   VQ_LAUNCH_CHECK();
+  if (n_chunks > 2) {
+    if (vec4)
+      mp_fixup_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(browptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, dx,
+                                                        lddx, nullptr, nullptr, 0);
+    else
+      mp_fixup_kernel<1><<<grid, kMpWarps * 32, 0, s>>>(browptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, dx,
+                                                        lddx, nullptr, nullptr, 0);
+    VQ_LAUNCH_CHECK();
+  }
   return VQGNN_OK;
 }

@@ -4,6 +4,8 @@
 // row boundaries, so a power-law hub row is spread over many warps; `walk_rows` tracks the rows a chunk
 // crosses and tells the caller when a row (or the part of it inside the chunk) is complete.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace vqgnn {
@@ -81,7 +83,8 @@ struct EntryGroup {
 // Walks the CSR entries [eb, ee) starting in row r.  Calls
 //   body(group)            for every group of <= U entries of the current row,
 //   flush(row, whole)      when the row ends inside the chunk (whole = it also started inside, so no other
-//                          warp touches its output) and once, with whole = false, for a trailing partial row,
+//                          warp touches its output) and once, with whole = false, for a trailing partial row;
+//                          a flush taking (row, whole, rs, re) also receives the row's entry range [rs, re),
 //   pol.row_begin(row)     whenever the current row changes (before its first entry).
 // All control flow is warp-uniform.
 template <bool HAS_RV, class Policy, class Body, class Flush>
@@ -109,6 +112,10 @@ __device__ __forceinline__ void walk_rows(int eb, int ee, int r, int64_t R, cons
       if (HAS_RV) rv_l = __ldg(rval + e);
       if (c_l >= B) node_l = tail_node ? __ldg(tail_node + (c_l - B)) : (c_l - B);
     }
+    auto do_flush = [&](int row, bool whole) {
+      if constexpr (std::is_invocable_v<Flush&, int, bool, int, int>) flush(row, whole, rs, re);
+      else flush(row, whole);
+    };
     const int cnt = min(32, ee - bb);
     int j = 0;
     while (j < cnt) {
@@ -131,7 +138,7 @@ __device__ __forceinline__ void walk_rows(int eb, int ee, int r, int64_t R, cons
       j = jend;
       pending = true;
       if (bb + j == re) {  // row r is complete
-        flush(r, rs >= eb);
+        do_flush(r, rs >= eb);
         pending = false;
         if (bb + j >= ee) break;
         do {  // next non-empty row (empty rows keep the pre-initialised output)
@@ -147,7 +154,58 @@ __device__ __forceinline__ void walk_rows(int eb, int ee, int r, int64_t R, cons
       }
     }
   }
-  if (pending) flush(r, false);
+  if (pending) {
+    if constexpr (std::is_invocable_v<Flush&, int, bool, int, int>) flush(r, false, rs, re);
+    else flush(r, false);
+  }
+}
+
+// How a (partial) row output must be combined so that the result does not depend on the order in which warps
+// retire.  A row cut by ONE chunk boundary has two pieces: two REDs onto a zero-initialised output commute exactly
+// ((0 + a) + b == (0 + b) + a).  A row spanning >= 3 chunks would depend on the RED order: its pieces are stored in
+// a piece buffer (slot 1: the piece holding the row start, slot 0: any later piece) and summed in chunk order by the
+// fix-up kernel.
+enum PieceKind { kPieceWhole = 0, kPieceRed = 1, kPieceHubStart = 2, kPieceHubNext = 3 };
+__device__ __forceinline__ int piece_kind(bool whole, int rs, int re, int eb, int chunk) {
+  if (whole) return kPieceWhole;
+  const int fc = rs / chunk, lc = (re - 1) / chunk;
+  if (lc - fc <= 1) return kPieceRed;
+  return rs >= eb ? kPieceHubStart : kPieceHubNext;
+}
+
+// block-level fp64 reduction of the info partials; every block stores its partial, the last block to arrive adds
+// them in block order (fixed tree): the scalar is bit-stable
+__device__ __forceinline__ void info_reduce_ordered(double part, double* ws_part, unsigned int* ws_count,
+                                                    float info_scale, float* info) {
+  __shared__ double sh[kMpWarps];
+  __shared__ bool last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  part = warp_sum(part);
+  if (lane == 0) sh[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMpWarps; ++i) t += sh[i];
+    ws_part[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ws_count, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double t = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(ws_part + i);
+  t = warp_sum(t);
+  __syncthreads();
+  if (lane == 0) sh[warp] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+#pragma unroll
+    for (int i = 0; i < kMpWarps; ++i) total += sh[i];
+    *info = static_cast<float>(static_cast<double>(info_scale) * total);
+  }
 }
 
 // The gather-accumulate body shared by every SpMM-shaped kernel: for the lane's VEC columns starting at c0

@@ -11,8 +11,12 @@
 //   * maps lane = entry, accumulates lane-private partial sums for the row, and at the end of a row segment
 //     reduce-scatters the 64 partial sums across the warp (62 shuffles) into vector REDs on y / gq.
 // Work items = (branch group, block of 512-entry chunks), dealt round-robin to one persistent CTA per SM.
-//   y[r, k*4..]  += sum_e val[e] * feat_scale * O_k[code_k(node[e]), :4]
-//   gq[r, k*4..] += sum_e rval[e]            * O_k[code_k(node[e]), 4:8]     ; info += <x[r], gq partial>
+//   yt[r, k*4..] = sum_e val[e] * feat_scale * O_k[code_k(node[e]), :4]
+//   gq[r, k*4..] = sum_e rval[e]            * O_k[code_k(node[e]), 4:8]
+// then (mp_tail_finish_kernel)  y += yt ;  info = info_scale * sum_r <x[r], gq[r]>.
+// Deterministic: a row segment wholly inside a chunk is stored, a row cut once is two REDs onto zero (they commute),
+// the pieces of longer rows go through the piece buffer + mp_tail_fixup_kernel in chunk order; the info scalar is an
+// ordered two-level reduction.  Which warp runs which chunk (dynamic scheduling) therefore cannot change a bit.
 #include "mp_common.cuh"
 
 namespace vqgnn {
@@ -65,9 +69,8 @@ __global__ void __launch_bounds__(kTailThreads, 1)
                         const float* __restrict__ val, const float* __restrict__ rval,
                         const int32_t* __restrict__ chunk_row, int n_chunks, int chunk, int nnz,
                         const int32_t* __restrict__ d_nnz, int B, const int16_t* __restrict__ codes_g, int64_t N, const float* __restrict__ O, int nb, int M,
-                        const float* __restrict__ x, int64_t ldx, float feat_scale, float* __restrict__ y,
-                        int64_t ldy, float* __restrict__ gq, int64_t ldgq, float* __restrict__ info,
-                        float info_scale, double* ws_sum, unsigned int* ws_count, int ng, int cpi,
+                        float feat_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ gq, int64_t ldgq,
+                        float* __restrict__ py, float* __restrict__ pgq, int C, int ng, int cpi,
                         int items_per_group) {
   extern __shared__ __align__(128) unsigned char cb_smem[];  // [G][M] codewords of 32 B, 16 B chunks swizzled
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,7 +82,6 @@ __global__ void __launch_bounds__(kTailThreads, 1)
     nnz = __ldg(d_nnz);
     n_chunks = (nnz + chunk - 1) / chunk;
   }
-  float fpart = 0.f;
   int loaded = -1;
   const int n_items = ng * items_per_group;
 
@@ -119,8 +121,23 @@ __global__ void __launch_bounds__(kTailThreads, 1)
       int r = __ldg(chunk_row + ch);
       int rbase = r;
       int rp_l = __ldg(rowptr + min(rbase + lane, B));
-      int re = __shfl_sync(0xffffffffu, rp_l, 1);
+      int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
       bool pending = false;
+      // emit the reduced sums of the current row segment (lane L holds columns 2L, 2L+1 of the group's 64)
+      auto emit = [&](float o0, float o1, bool whole) {
+        const int gI = lane >> 2, jj = (lane & 3) * 2;
+        if (gI >= gcount) return;
+        const int colbase = (kbase + gI) * 4 + (jj & 3);
+        const int kind = piece_kind(whole, rs, re, eb, chunk);
+        const int64_t poff = (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + colbase;
+        float* dst = jj < 4 ? y + static_cast<int64_t>(r) * ldy + colbase
+                            : (gq ? gq + static_cast<int64_t>(r) * ldgq + colbase : nullptr);
+        float* pdst = (jj < 4 ? py : pgq) + poff;
+        if (!dst) return;
+        if (kind == kPieceWhole) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
+        else if (kind == kPieceRed) red_v2(dst, o0, o1);
+        else *reinterpret_cast<float2*>(pdst) = make_float2(o0, o1);
+      };
 
       // software pipeline: (node, val, rval) two batches ahead, codes one batch ahead
       int node_n = 0;
@@ -184,19 +201,7 @@ __global__ void __launch_bounds__(kTailThreads, 1)
           if (pend == re) {  // row r complete: reduce over lanes and accumulate into the outputs
             float o0, o1;
             warp_reduce_scatter64(acc, lane, o0, o1);
-            const int gI = lane >> 2, jj = (lane & 3) * 2;
-            if (gI < gcount) {
-              const int colbase = (kbase + gI) * 4 + (jj & 3);
-              if (jj < 4) {
-                red_v2(y + static_cast<int64_t>(r) * ldy + colbase, o0, o1);
-              } else {
-                if (gq) red_v2(gq + static_cast<int64_t>(r) * ldgq + colbase, o0, o1);
-                if (info) {
-                  const float2 xr = __ldg(reinterpret_cast<const float2*>(x + static_cast<int64_t>(r) * ldx + colbase));
-                  fpart = fmaf(xr.x, o0, fmaf(xr.y, o1, fpart));
-                }
-              }
-            }
+            emit(o0, o1, rs >= eb);
 #pragma unroll
             for (int i = 0; i < 64; ++i) acc[i] = 0.f;
             pending = false;
@@ -207,6 +212,7 @@ __global__ void __launch_bounds__(kTailThreads, 1)
                 rbase = r;
                 rp_l = __ldg(rowptr + min(rbase + lane, B));
               }
+              rs = __shfl_sync(0xffffffffu, rp_l, r - rbase);
               re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
             } while (re <= j0);
           }
@@ -215,42 +221,72 @@ __global__ void __launch_bounds__(kTailThreads, 1)
       if (pending) {
         float o0, o1;
         warp_reduce_scatter64(acc, lane, o0, o1);
-        const int gI = lane >> 2, jj = (lane & 3) * 2;
-        if (gI < gcount) {
-          const int colbase = (kbase + gI) * 4 + (jj & 3);
-          if (jj < 4) {
-            red_v2(y + static_cast<int64_t>(r) * ldy + colbase, o0, o1);
-          } else {
-            if (gq) red_v2(gq + static_cast<int64_t>(r) * ldgq + colbase, o0, o1);
-            if (info) {
-              const float2 xr = __ldg(reinterpret_cast<const float2*>(x + static_cast<int64_t>(r) * ldx + colbase));
-              fpart = fmaf(xr.x, o0, fmaf(xr.y, o1, fpart));
-            }
-          }
-        }
+        emit(o0, o1, false);
       }
     }
   }
+}
 
-  if (info) {  // CTA reduction of the info partials, "last CTA finishes"
-    __shared__ double sh[kTailWarps];
-    double part = warp_sum(static_cast<double>(fpart));
-    __syncthreads();
-    if (lane == 0) sh[warp] = part;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-#pragma unroll
-      for (int i = 0; i < kTailWarps; ++i) t += sh[i];
-      atomicAdd(ws_sum, t);
-      __threadfence();
-      const unsigned int ticket = atomicAdd(ws_count, 1u);
-      if (ticket == gridDim.x - 1) {
-        const double total = atomicAdd(ws_sum, 0.0);
-        atomicAdd(info, static_cast<float>(static_cast<double>(info_scale) * total));
+// pieces of rows spanning >= 3 chunks, summed in chunk order: thread = (chunk c, float2 column pair)
+__global__ void __launch_bounds__(256)
+    mp_tail_fixup_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ chunk_row, int n_chunks,
+                         int chunk, const int32_t* __restrict__ d_nnz, int B, int C, const float* __restrict__ py,
+                         float* __restrict__ y, int64_t ldy, const float* __restrict__ pgq, float* __restrict__ gq,
+                         int64_t ldgq) {
+  if (d_nnz) n_chunks = (__ldg(d_nnz) + chunk - 1) / chunk;
+  const int half = C / 2;
+  const int64_t total = static_cast<int64_t>(n_chunks) * half;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = static_cast<int>(i / half);
+    const int col = static_cast<int>(i - static_cast<int64_t>(c) * half) * 2;
+    if (c + 2 >= n_chunks) continue;
+    const int r = __ldg(chunk_row + c + 1);
+    if (r >= B) continue;
+    const int64_t rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+    if (rs < static_cast<int64_t>(c) * chunk || rs >= static_cast<int64_t>(c + 1) * chunk) continue;
+    const int lc = static_cast<int>((re - 1) / chunk);
+    if (lc < c + 2) continue;
+    float2 a = *reinterpret_cast<const float2*>(py + (static_cast<int64_t>(c) * 2 + 1) * C + col);
+    float2 q = make_float2(0.f, 0.f);
+    if (gq) q = *reinterpret_cast<const float2*>(pgq + (static_cast<int64_t>(c) * 2 + 1) * C + col);
+    for (int cc = c + 1; cc <= lc; ++cc) {
+      const float2 t = *reinterpret_cast<const float2*>(py + static_cast<int64_t>(cc) * 2 * C + col);
+      a.x += t.x, a.y += t.y;
+      if (gq) {
+        const float2 u = *reinterpret_cast<const float2*>(pgq + static_cast<int64_t>(cc) * 2 * C + col);
+        q.x += u.x, q.y += u.y;
       }
     }
+    *reinterpret_cast<float2*>(y + static_cast<int64_t>(r) * ldy + col) = a;
+    if (gq) *reinterpret_cast<float2*>(gq + static_cast<int64_t>(r) * ldgq + col) = q;
   }
+}
+
+// y += yt ; info = info_scale * sum <x, gq>  (ordered two-level reduction)
+__global__ void __launch_bounds__(256)
+    mp_tail_finish_kernel(int64_t B, int C, const float* __restrict__ yt, float* __restrict__ y, int64_t ldy,
+                          const float* __restrict__ x, int64_t ldx, const float* __restrict__ gq, int64_t ldgq,
+                          float* __restrict__ info, float info_scale, double* ws_part, unsigned int* ws_count) {
+  const int half = C / 2;
+  const int64_t total = B * half;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  double part = 0.0;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / half;
+    const int col = static_cast<int>(i - r * half) * 2;
+    float2* yp = reinterpret_cast<float2*>(y + r * ldy + col);
+    const float2 t = *reinterpret_cast<const float2*>(yt + r * C + col);
+    float2 v = *yp;
+    v.x += t.x, v.y += t.y;
+    *yp = v;
+    if (info) {
+      const float2 xr = __ldg(reinterpret_cast<const float2*>(x + r * ldx + col));
+      const float2 g = *reinterpret_cast<const float2*>(gq + r * ldgq + col);
+      part += static_cast<double>(fmaf(xr.x, g.x, xr.y * g.y));
+    }
+  }
+  if (info) info_reduce_ordered(part, ws_part, ws_count, info_scale, info);
 }
 
 // codes_g[(k / G) * N + node][k % G] = codes[node, k] for the listed nodes (all N when rows == nullptr)
@@ -274,6 +310,7 @@ __global__ void codes_owner_kernel(const int32_t* __restrict__ nodes, int64_t n,
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n; e += stride) {
     const int32_t nd = __ldg(nodes + e);
+    if (nd < 0) continue;  // padding of a short batch (dist.allgather_code_updates capacity)
     if (phase == 0) owner[nd] = -1;
     else atomicMax(owner + nd, static_cast<int32_t>(e));
   }
@@ -288,7 +325,7 @@ __global__ void codes_apply_kernel(const int32_t* __restrict__ nodes, const int1
     const int64_t e = i / nbc;
     const int j = static_cast<int>(i - e * nbc);
     const int64_t nd = __ldg(nodes + e);
-    if (__ldg(owner + nd) != e) continue;
+    if (nd < 0 || __ldg(owner + nd) != e) continue;
     const int k = k0 + j;
     const int16_t cv = __ldg(new_codes + i);
     codes[nd * nb + k] = cv;
@@ -337,6 +374,16 @@ extern "C" int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* ro
   return VQGNN_OK;
 }
 
+static inline size_t tl_al256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+constexpr int kTailFinishGrid = 4 * kNumSMs;
+
+// workspace: [count 256 B][finish-kernel partials][yt B*C][y pieces n_chunks*2*C][gq pieces n_chunks*2*C]
+extern "C" size_t vqgnn_mp_fwd_tail_workspace_bytes(int64_t nnz, int chunk, int64_t B, int C) {
+  const int64_t n_chunks = chunk > 0 ? (nnz + chunk - 1) / chunk : 0;
+  return 512 + tl_al256(static_cast<size_t>(kTailFinishGrid) * 8) + tl_al256(static_cast<size_t>(B) * C * 4) +
+         2 * tl_al256(static_cast<size_t>(n_chunks) * 2 * C * 4);
+}
+
 extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, const float* val, const float* rval,
                                  const int32_t* chunk_row, int chunk, int64_t nnz, const int32_t* d_nnz, int64_t B,
                                  const float* x, int64_t ldx, const int16_t* codes_g, int64_t N, const float* O, int nb, int M,
@@ -351,31 +398,53 @@ extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, con
                    (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
                    (!gq || (reinterpret_cast<uintptr_t>(gq) & 7) == 0),
                "mp_fwd_tail: operands must be 8 B aligned with even leading dimensions");
-  VQ_CHECK_ARG(!info || ws, "mp_fwd_tail: info needs a workspace");
+  VQ_CHECK_ARG(ws, "mp_fwd_tail: needs a workspace of vqgnn_mp_fwd_tail_workspace_bytes() bytes");
+  VQ_CHECK_ARG(!info || gq, "mp_fwd_tail: info needs gq");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int n_chunks = static_cast<int>((nnz + chunk - 1) / chunk);
-  if (n_chunks == 0) return VQGNN_OK;
+  const int C = nb * D;
+  if (n_chunks == 0) {
+    if (gq)
+      if (int rc = zero_rows(gq, B, C, ldgq, s)) return rc;
+    if (info) VQ_CUDA(cudaMemsetAsync(info, 0, sizeof(float), s));
+    return VQGNN_OK;
+  }
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+  unsigned int* ws_count = reinterpret_cast<unsigned int*>(p);
+  double* ws_part = reinterpret_cast<double*>(p + 256);
+  float* yt = reinterpret_cast<float*>(p + 256 + tl_al256(static_cast<size_t>(kTailFinishGrid) * 8));
+  float* py = yt + tl_al256(static_cast<size_t>(B) * C * 4) / 4;
+  float* pgq = py + tl_al256(static_cast<size_t>(n_chunks) * 2 * C * 4) / 4;
+  VQ_CUDA(cudaMemsetAsync(ws_count, 0, 16, s));
+  VQ_CUDA(cudaMemsetAsync(yt, 0, sizeof(float) * B * C, s));
+  if (gq)
+    if (int rc = zero_rows(gq, B, C, ldgq, s)) return rc;
   const int ng = (nb + G - 1) / G;
   // items = (group, block of cpi chunks): ~8 items per CTA, dealt round-robin
   const int grid = kNumSMs;
   int items_per_group = std::max(1, (grid * 8 + ng - 1) / ng);
   int cpi = std::max(kTailWarps, (n_chunks + items_per_group - 1) / items_per_group);
   items_per_group = (n_chunks + cpi - 1) / cpi;
-  double* ws_sum = static_cast<double*>(ws);
-  unsigned int* ws_count = ws ? reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + 8) : nullptr;
-  if (info) VQ_CUDA(cudaMemsetAsync(ws, 0, 16, s));
   const size_t smem = static_cast<size_t>(G) * M * 32 + 128;
 #define VQ_TAIL(GG)                                                                                           \
   do {                                                                                                        \
     auto kern = mp_tail_smem_kernel<GG>;                                                                      \
     VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
     kern<<<std::min(grid, ng * items_per_group), kTailThreads, smem, s>>>(                                    \
-        rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, d_nnz, (int)B, codes_g, N, O, nb, M, x, ldx, \
-        feat_scale, y, ldy, gq, ldgq, info, info_scale, ws_sum, ws_count, ng, cpi, items_per_group);          \
+        rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, d_nnz, (int)B, codes_g, N, O, nb, M,   \
+        feat_scale, yt, (int64_t)C, gq, ldgq, py, pgq, C, ng, cpi, items_per_group);                          \
   } while (0)
   if (G == 8) VQ_TAIL(8);
   else VQ_TAIL(6);
 #undef VQ_TAIL
+  VQ_LAUNCH_CHECK();
+  const int64_t fx = static_cast<int64_t>(n_chunks) * (C / 2);
+  mp_tail_fixup_kernel<<<static_cast<int>(std::min<int64_t>((fx + 255) / 256, 8 * kNumSMs)), 256, 0, s>>>(
+      rowptr, chunk_row, n_chunks, chunk, d_nnz, (int)B, C, py, yt, C, pgq, gq, ldgq);
+  VQ_LAUNCH_CHECK();
+  const int64_t tot = B * (C / 2);
+  const int fgrid = static_cast<int>(std::min<int64_t>((tot + 255) / 256, kTailFinishGrid));
+  mp_tail_finish_kernel<<<fgrid, 256, 0, s>>>(B, C, yt, y, ldy, x, ldx, gq, ldgq, info, info_scale, ws_part, ws_count);
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }

@@ -8,6 +8,12 @@
 //   in-batch part : A_BB (+ its transpose for GCN = to_symmetric, + self loops deg_inv, doubled for GCN), as a CSR
 //                   by row (forward) and by column (backward)
 // HBM-bound integer work: warp-aggregated counting + cursor scatter, two small single-CTA scans.
+//
+// Determinism: the ORDER of the entries inside a CSR row decides the order of the fp32 sums in the message-passing
+// kernels, so nothing here may depend on which warp wins an atomic: the tail part is a STABLE compaction of the
+// row-sorted A_BN (two-level prefix sum, no cursors), and every cursor-scattered CSR (in-batch forward / transposed,
+// v2 transposed) is finished by sorting each row segment by its unique key (seg_sort_*: shuffle / rank sort for
+// short segments, shared- or global-memory bitonic network for long ones).  Counts are integer atomics (exact).
 #include "common.cuh"
 
 namespace vqgnn {
@@ -33,33 +39,177 @@ __device__ __forceinline__ int warp_slot(int* counters, int key, bool flag) {
   return slot;
 }
 
-// pass 1 (count) / pass 2 (scatter) over A_BN
-template <bool SCATTER>
+// pass 1 over A_BN: per-row tail counts (integer atomics) + per-tile tail counts; tile = kTailTile consecutive entries
+constexpr int kTailTile = 2048;
+
 __global__ void __launch_bounds__(256)
-    plan_tail_kernel(const int64_t* __restrict__ r, const int64_t* __restrict__ c, const float* __restrict__ v,
-                     const float* __restrict__ rv, int64_t nnz, const int32_t* __restrict__ pos, int has_bb,
-                     int* __restrict__ counters /* count: row_cnt[B]; scatter: cursor[B] */,
-                     const int32_t* __restrict__ t_rowptr, int32_t* __restrict__ t_node,
-                     float* __restrict__ t_val, float* __restrict__ t_rval) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t n_round = (nnz + 31) / 32 * 32;  // keep warps converged for the warp-wide intrinsics
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_round; e += stride) {
+    plan_tail_count_kernel(const int64_t* __restrict__ r, const int64_t* __restrict__ c, int64_t nnz,
+                           const int32_t* __restrict__ pos, int has_bb, int* __restrict__ row_cnt,
+                           int* __restrict__ tile_cnt) {
+  __shared__ int tot;
+  if (threadIdx.x == 0) tot = 0;
+  __syncthreads();
+  const int64_t e0 = static_cast<int64_t>(blockIdx.x) * kTailTile;
+  int mine = 0;
+  for (int i = threadIdx.x; i < kTailTile; i += 256) {   // warps stay converged: kTailTile % 256 == 0
+    const int64_t e = e0 + i;
     bool tail = false;
     int row = 0;
+    if (e < nnz) {
+      row = static_cast<int>(r[e]);
+      tail = !has_bb || __ldg(pos + c[e]) < 0;
+    }
+    warp_slot(row_cnt, row, tail);
+    mine += tail;
+  }
+  mine = static_cast<int>(warp_sum(static_cast<float>(mine)));   // <= 2048: exact in fp32
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&tot, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = tot;
+}
+
+// pass 2: stable compaction -- entry e lands at tile_off[tile] + (number of earlier tail entries of its tile), so the
+// output keeps A_BN's order (row-sorted input => row-grouped output matching t_rowptr)
+__global__ void __launch_bounds__(256)
+    plan_tail_scatter_kernel(const int64_t* __restrict__ r, const int64_t* __restrict__ c,
+                             const float* __restrict__ v, const float* __restrict__ rv, int64_t nnz,
+                             const int32_t* __restrict__ pos, int has_bb, const int32_t* __restrict__ tile_off,
+                             int32_t* __restrict__ t_node, float* __restrict__ t_val, float* __restrict__ t_rval) {
+  __shared__ int wtot[8];
+  __shared__ int base_sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_sh = __ldg(tile_off + blockIdx.x);
+  __syncthreads();
+  const int64_t e0 = static_cast<int64_t>(blockIdx.x) * kTailTile;
+  for (int i0 = 0; i0 < kTailTile; i0 += 256) {
+    const int64_t e = e0 + i0 + threadIdx.x;
+    bool tail = false;
     int64_t col = 0;
     if (e < nnz) {
       col = c[e];
-      row = static_cast<int>(r[e]);
       tail = !has_bb || __ldg(pos + col) < 0;
     }
-    const int slot = warp_slot(counters, row, tail);
-    if (SCATTER && tail) {
-      const int64_t dst = static_cast<int64_t>(__ldg(t_rowptr + row)) + slot;
+    const unsigned m = __ballot_sync(0xffffffffu, tail);
+    if (lane == 0) wtot[warp] = __popc(m);
+    __syncthreads();
+    int before = base_sh;
+    for (int w = 0; w < warp; ++w) before += wtot[w];
+    if (tail) {
+      const int64_t dst = before + __popc(m & ((1u << lane) - 1));
       t_node[dst] = static_cast<int32_t>(col);
       t_val[dst] = v[e];
       t_rval[dst] = rv ? rv[e] : 0.f;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += wtot[w];
+      base_sh += t;
+    }
+    __syncthreads();
   }
+}
+
+// ---- per-segment sort of (key, val) pairs by key (keys are unique inside a segment): src -> dst -----------------
+// short segments: one warp each
+__global__ void __launch_bounds__(256)
+    seg_sort_short_kernel(const int32_t* __restrict__ ptr, int nseg, const int32_t* __restrict__ ksrc,
+                          const float* __restrict__ vsrc, int32_t* __restrict__ kdst, float* __restrict__ vdst,
+                          int max_short) {
+  const int lane = threadIdx.x & 31;
+  for (int sg = blockIdx.x * 8 + (threadIdx.x >> 5); sg < nseg; sg += gridDim.x * 8) {
+    const int s0 = __ldg(ptr + sg), n = __ldg(ptr + sg + 1) - s0;
+    if (n <= 0 || n > max_short) continue;
+    if (n <= 32) {
+      const int k = lane < n ? ksrc[s0 + lane] : 0x7fffffff;
+      const float v = lane < n ? vsrc[s0 + lane] : 0.f;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const int kj = __shfl_sync(0xffffffffu, k, j);
+        rank += (kj < k) || (kj == k && j < lane);
+      }
+      if (lane < n) kdst[s0 + rank] = k, vdst[s0 + rank] = v;
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        const int k = ksrc[s0 + i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+          const int kj = __ldg(ksrc + s0 + j);
+          rank += (kj < k) || (kj == k && j < i);
+        }
+        kdst[s0 + rank] = k, vdst[s0 + rank] = vsrc[s0 + i];
+      }
+    }
+  }
+}
+
+// long segments: one CTA each, normalised bitonic network (every compare-exchange moves the smaller key down, so the
+// virtual +inf padding above n never moves); in shared memory up to kSegSmem pairs, in place in dst beyond that
+constexpr int kSegSmem = 8192;
+
+__device__ __forceinline__ void seg_cmpx(int32_t* k, float* v, int i, int l, int n) {
+  if (l < n) {
+    const int ki = k[i], kl = k[l];
+    if (kl < ki) {
+      const float vi = v[i];
+      k[i] = kl, v[i] = v[l];
+      k[l] = ki, v[l] = vi;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+    seg_sort_long_kernel(const int32_t* __restrict__ ptr, int nseg, const int32_t* __restrict__ ksrc,
+                         const float* __restrict__ vsrc, int32_t* __restrict__ kdst, float* __restrict__ vdst,
+                         int max_short) {
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  int32_t* ks = reinterpret_cast<int32_t*>(seg_smem);
+  float* vs = reinterpret_cast<float*>(seg_smem + sizeof(int32_t) * kSegSmem);
+  for (int sg = blockIdx.x; sg < nseg; sg += gridDim.x) {
+    const int s0 = __ldg(ptr + sg), n = __ldg(ptr + sg + 1) - s0;
+    if (n <= max_short) continue;
+    const bool in_smem = n <= kSegSmem;
+    int32_t* k = in_smem ? ks : kdst + s0;
+    float* v = in_smem ? vs : vdst + s0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) k[i] = ksrc[s0 + i], v[i] = vsrc[s0 + i];
+    __syncthreads();
+    int np = 1;
+    while (np < n) np <<= 1;
+    for (int kk = 2; kk <= np; kk <<= 1) {
+      for (int t = threadIdx.x; t < np / 2; t += blockDim.x) {   // flip step: i <-> i ^ (kk - 1)
+        const int blk = t / (kk / 2), o = t - blk * (kk / 2);
+        const int i = blk * kk + o;
+        seg_cmpx(k, v, i, i ^ (kk - 1), n);
+      }
+      __syncthreads();
+      for (int j = kk >> 2; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < np / 2; t += blockDim.x) {
+          const int i = ((t / j) * 2 * j) + (t % j);
+          seg_cmpx(k, v, i, i + j, n);
+        }
+        __syncthreads();
+      }
+    }
+    if (in_smem)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) kdst[s0 + i] = ks[i], vdst[s0 + i] = vs[i];
+  }
+}
+
+constexpr int kSegShortMax = 128;
+
+static int seg_sort(const int32_t* ptr, int nseg, const int32_t* ksrc, const float* vsrc, int32_t* kdst, float* vdst,
+                    cudaStream_t s) {
+  if (nseg <= 0) return VQGNN_OK;
+  const int g1 = std::min((nseg + 7) / 8, 32 * kNumSMs);
+  seg_sort_short_kernel<<<g1, 256, 0, s>>>(ptr, nseg, ksrc, vsrc, kdst, vdst, kSegShortMax);
+  VQ_LAUNCH_CHECK();
+  const size_t smem = static_cast<size_t>(kSegSmem) * 8;
+  VQ_CUDA(cudaFuncSetAttribute(seg_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  seg_sort_long_kernel<<<std::min(nseg, 4 * kNumSMs), 1024, smem, s>>>(ptr, nseg, ksrc, vsrc, kdst, vdst, kSegShortMax);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
 }
 
 // in-batch entries: A_BB (+ transposes) + self loops.  KEY 0: by row (forward CSR), 1: by column (transposed)
@@ -185,8 +335,12 @@ static int plan_grid(int64_t n) { return static_cast<int>(std::min<int64_t>((n +
 
 using namespace vqgnn;
 
-extern "C" size_t vqgnn_plan_v1_workspace_bytes(int64_t N, int64_t B) {
-  return static_cast<size_t>(N) * 4 + static_cast<size_t>(B) * 4 * 3 + 64;
+static inline size_t al256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+extern "C" size_t vqgnn_plan_v1_workspace_bytes(int64_t N, int64_t B, int64_t nnz, int64_t nin) {
+  const size_t tiles = static_cast<size_t>((nnz + kTailTile - 1) / kTailTile) + 1;
+  return al256(static_cast<size_t>(N) * 4) + al256(static_cast<size_t>(B) * 4 * 3) + 2 * al256(tiles * 4) +
+         4 * al256(static_cast<size_t>(nin > 0 ? nin : 1) * 4) + 256;
 }
 
 extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const float* v, const float* rv, int64_t nnz,
@@ -206,10 +360,24 @@ extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const flo
   VQ_CHECK_ARG(!self_loops || deg_inv, "plan_v1_build: self loops need deg_inv");
   VQ_CHECK_ARG(tail_chunk > 0 && tail_chunk % 32 == 0 && chunk > 0 && chunk % 32 == 0, "plan_v1_build: bad chunk sizes");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int32_t* pos = static_cast<int32_t*>(ws);
-  int* cnt_t = reinterpret_cast<int*>(pos + N);
+  const int64_t nin = nbb * (symmetric ? 2 : 1) + (self_loops ? B : 0);
+  const int tiles = static_cast<int>((nnz + kTailTile - 1) / kTailTile);
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+  int32_t* pos = reinterpret_cast<int32_t*>(p);
+  p += al256(static_cast<size_t>(N) * 4);
+  int* cnt_t = reinterpret_cast<int*>(p);
   int* cnt_r = cnt_t + B;
   int* cnt_c = cnt_r + B;
+  p += al256(static_cast<size_t>(B) * 4 * 3);
+  int* tile_cnt = reinterpret_cast<int*>(p);
+  p += al256(static_cast<size_t>(tiles + 1) * 4);
+  int32_t* tile_off = reinterpret_cast<int32_t*>(p);
+  p += al256(static_cast<size_t>(tiles + 1) * 4);
+  const size_t an = al256(static_cast<size_t>(nin > 0 ? nin : 1) * 4);
+  int32_t* tmp_ic = reinterpret_cast<int32_t*>(p);
+  float* tmp_iv = reinterpret_cast<float*>(p + an);
+  int32_t* tmp_br = reinterpret_cast<int32_t*>(p + 2 * an);
+  float* tmp_bv = reinterpret_cast<float*>(p + 3 * an);
   const int has_bb = bb_r != nullptr;   // A_BB == None (eval / no recovery): every neighbour goes through its codeword
   if (has_bb) {
     VQ_CUDA(cudaMemsetAsync(pos, 0xFF, sizeof(int32_t) * N, s));
@@ -217,16 +385,17 @@ extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const flo
     VQ_LAUNCH_CHECK();
   }
   VQ_CUDA(cudaMemsetAsync(cnt_t, 0, sizeof(int) * B * 3, s));
-  // ---- tail part
-  const int tgrid = plan_grid(nnz);
+  // ---- tail part: per-row counts -> t_rowptr; per-tile counts -> stable positions
   if (nnz > 0) {
-    plan_tail_kernel<false><<<tgrid, 256, 0, s>>>(r, c, v, rv, nnz, pos, has_bb, cnt_t, nullptr, nullptr, nullptr, nullptr);
+    plan_tail_count_kernel<<<tiles, 256, 0, s>>>(r, c, nnz, pos, has_bb, cnt_t, tile_cnt);
     VQ_LAUNCH_CHECK();
   }
   plan_scan_kernel<<<1, 1024, 0, s>>>(cnt_t, (int)B, t_rowptr, t_count);
   VQ_LAUNCH_CHECK();
   if (nnz > 0) {
-    plan_tail_kernel<true><<<tgrid, 256, 0, s>>>(r, c, v, rv, nnz, pos, has_bb, cnt_t, t_rowptr, t_node, t_val, t_rval);
+    plan_scan_kernel<<<1, 1024, 0, s>>>(tile_cnt, tiles, tile_off, nullptr);
+    VQ_LAUNCH_CHECK();
+    plan_tail_scatter_kernel<<<tiles, 256, 0, s>>>(r, c, v, rv, nnz, pos, has_bb, tile_off, t_node, t_val, t_rval);
     VQ_LAUNCH_CHECK();
   }
   const int max_chunks = static_cast<int>((nnz + tail_chunk - 1) / tail_chunk);
@@ -235,8 +404,7 @@ extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const flo
                                                                         max_chunks, t_chunk_row);
     VQ_LAUNCH_CHECK();
   }
-  // ---- in-batch part (forward by row, backward by column)
-  const int64_t nin = nbb * (symmetric ? 2 : 1) + (self_loops ? B : 0);
+  // ---- in-batch part (forward by row, backward by column): cursor scatter into scratch, then per-row sort
   if (nin > 0) {
     VQ_CHECK_ARG(i_col && i_val && b_row && b_val, "plan_v1_build: in-batch outputs missing");
     const int igrid = plan_grid(nin);
@@ -250,15 +418,20 @@ extern "C" int vqgnn_plan_v1_build(const int64_t* r, const int64_t* c, const flo
   VQ_LAUNCH_CHECK();
   if (nin > 0) {
     plan_inb_kernel<true><<<plan_grid(nin), 256, 0, s>>>(bb_r, bb_c, bb_v, nbb, deg_inv, (int)B, symmetric, self_loops,
-                                                         cnt_r, cnt_c, i_rowptr, i_col, i_val, b_rowptr, b_row, b_val);
+                                                         cnt_r, cnt_c, i_rowptr, tmp_ic, tmp_iv, b_rowptr, tmp_br,
+                                                         tmp_bv);
     VQ_LAUNCH_CHECK();
+    if (int rc = seg_sort(i_rowptr, (int)B, tmp_ic, tmp_iv, i_col, i_val, s)) return rc;
+    if (int rc = seg_sort(b_rowptr, (int)B, tmp_br, tmp_bv, b_row, b_val, s)) return rc;
     if (int rc = vqgnn_mp_chunk_rows(i_rowptr, B, nin, chunk, i_chunk_row, stream)) return rc;
     if (int rc = vqgnn_mp_chunk_rows(b_rowptr, B, nin, chunk, b_chunk_row, stream)) return rc;
   }
   return VQGNN_OK;
 }
 
-extern "C" size_t vqgnn_csr_transpose_workspace_bytes(int64_t B) { return static_cast<size_t>(B) * 4 + 64; }
+extern "C" size_t vqgnn_csr_transpose_workspace_bytes(int64_t B, int64_t nnz) {
+  return al256(static_cast<size_t>(B) * 4) + 2 * al256(static_cast<size_t>(nnz > 0 ? nnz : 1) * 4) + 256;
+}
 
 extern "C" int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col, const float* val, int64_t R,
                                       int64_t nnz, int64_t B, int32_t* browptr, int32_t* brow, float* bval,
@@ -268,7 +441,12 @@ extern "C" int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col,
                "csr_transpose_lt: bad arguments");
   VQ_CHECK_ARG(nnz == 0 || (col && val && brow && bval), "csr_transpose_lt: null arrays");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int* cnt = static_cast<int*>(ws);
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+  int* cnt = reinterpret_cast<int*>(p);
+  p += al256(static_cast<size_t>(B) * 4);
+  const size_t an = al256(static_cast<size_t>(nnz > 0 ? nnz : 1) * 4);
+  int32_t* tmp_r = reinterpret_cast<int32_t*>(p);
+  float* tmp_v = reinterpret_cast<float*>(p + an);
   VQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * B, s));
   const int grid = static_cast<int>(std::min<int64_t>((R + 7) / 8, 16 * kNumSMs));
   if (nnz > 0) {
@@ -278,8 +456,10 @@ extern "C" int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col,
   plan_scan_kernel<<<1, 1024, 0, s>>>(cnt, (int)B, browptr, count);
   VQ_LAUNCH_CHECK();
   if (nnz > 0) {
-    plan_transpose_kernel<true><<<grid, 256, 0, s>>>(rowptr, col, val, (int)R, (int)B, cnt, browptr, brow, bval);
+    plan_transpose_kernel<true><<<grid, 256, 0, s>>>(rowptr, col, val, (int)R, (int)B, cnt, browptr, tmp_r, tmp_v);
     VQ_LAUNCH_CHECK();
+    // the cursor scatter leaves every column's entries in atomic order: sort them by source row (unique)
+    if (int rc = seg_sort(browptr, (int)B, tmp_r, tmp_v, brow, bval, s)) return rc;
   }
   return VQGNN_OK;
 }

@@ -6,14 +6,15 @@ namespace vqgnn {
 
 // ------------------------------------------------------------------------------------------------
 // (1) column moments, fp64 accumulation.  HBM-bound: reads x (and g) once.
-// block = (32 columns, 8 row lanes); grid = (row tiles, column tiles)
+// block = (32 columns, 8 row lanes); grid = (row tiles, column tiles).  Two levels, no atomics: every row tile
+// writes its partial sums, vq_moments_reduce_kernel adds the tiles in index order (bit-stable results).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMomRowsPerBlock = 512;
 
 __global__ void __launch_bounds__(256) vq_moments_kernel(const float* __restrict__ x, int64_t ldx,
                                                          const float* __restrict__ g, int64_t ldg,
                                                          int64_t B, int C, int Cg, int tilesC,
-                                                         double* __restrict__ sums) {
+                                                         double* __restrict__ part) {
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ctile = blockIdx.y;
   const float* src;
@@ -41,9 +42,18 @@ __global__ void __launch_bounds__(256) vq_moments_kernel(const float* __restrict
   if (ty == 0 && c < width) {
 #pragma unroll
     for (int i = 1; i < 8; ++i) s1 += sh1[i][tx], s2 += sh2[i][tx];
-    atomicAdd(sums + out_c, s1);
-    atomicAdd(sums + Ctot + out_c, s2);
+    double* dst = part + static_cast<int64_t>(blockIdx.x) * 2 * Ctot;
+    dst[out_c] = s1;
+    dst[Ctot + out_c] = s2;
   }
+}
+
+__global__ void vq_moments_reduce_kernel(const double* __restrict__ part, int tiles, int n, double* __restrict__ sums) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double t = 0.0;
+  for (int i = 0; i < tiles; ++i) t += part[static_cast<int64_t>(i) * n + c];
+  sums[c] = t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -53,8 +63,8 @@ __global__ void vq_whiten_kernel(const double* __restrict__ sums, double count, 
                                  int has_grad, float* run_mean_f, float* run_var_f, float* run_mean_g,
                                  float* run_var_g, float eps_f, float mom_f, float eps_g, float mom_g,
                                  float gs0, float gs1, int training, int seed_running,
-                                 int64_t* nbt_f, int64_t* nbt_g, float* __restrict__ scale,
-                                 float* __restrict__ shift) {
+                                 const int32_t* __restrict__ seed_mask, int64_t* nbt_f, int64_t* nbt_g,
+                                 float* __restrict__ scale, float* __restrict__ shift) {
   const int C = nb * D, Cg = has_grad ? nb * Dg : 0, Ctot = C + Cg;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Ctot) return;
@@ -69,7 +79,8 @@ __global__ void vq_whiten_kernel(const double* __restrict__ sums, double count, 
     gs = (d < D) ? gs0 : gs1;
   }
   float mean_f, var_f;  // statistics used to normalise (fp32, like ATen)
-  if (training) {
+  if (seed_mask) seed_running = seed_mask[is_g ? (c - C) / Dg : c / D];  // per branch (one bn_inited per quantiser)
+  if (training || seed_running) {
     if (d_count) count = *d_count;
     const double mean = sums[c] / count;
     double var_b = sums[Ctot + c] / count - mean * mean;
@@ -80,11 +91,16 @@ __global__ void vq_whiten_kernel(const double* __restrict__ sums, double count, 
     if (seed_running) {  // vq.py:216-221: running stats <- batch mean / unbiased var, then BN's own update
       m_run = mean_f, v_run = static_cast<float>(var_u);
     }
+    if (!training) {  // eval-mode update() on a fresh quantiser: seeded, then normalised with the running statistics
+      *rm = m_run, *rv = v_run;
+      mean_f = m_run, var_f = v_run;
+    } else {
     *rm = (1.f - mom) * m_run + mom * mean_f;
     *rv = (1.f - mom) * v_run + mom * static_cast<float>(var_u);
     // BatchNorm1d.num_batches_tracked += 1 per training forward (one counter per branch)
     if (!is_g && nbt_f && c % D == 0) nbt_f[c / D] += 1;
     if (is_g && nbt_g && (c - C) % Dg == 0) nbt_g[(c - C) / Dg] += 1;
+    }
   } else {
     mean_f = *rm, var_f = *rv;
   }
@@ -259,7 +275,12 @@ __global__ void __launch_bounds__(kFinThreads)
   }
   if (bad) atomicOr(&bad_sh, 1);
   __syncthreads();
-  if (tid == 0 && bad_sh) atomicOr(status, VQGNN_STATUS_BAD_INIT);
+  if (bad_sh) {
+    // vq.py:188-189 / 253-254 raise 'Bad Init!' BEFORE _ema_w / _embedding / _embedding_output are touched (the
+    // cluster sizes are already updated at that point): leave them as they are instead of dividing by zero
+    if (tid == 0) atomicOr(status, VQGNN_STATUS_BAD_INIT);
+    return;
+  }
 
   // ema_w, E, O
   const int W = D + Dg;
@@ -290,15 +311,23 @@ __global__ void __launch_bounds__(kFinThreads)
 
 using namespace vqgnn;
 
+extern "C" size_t vqgnn_vq_moments_workspace_bytes(int64_t B, int C, int Cg) {
+  return static_cast<size_t>(ceil_div(B, kMomRowsPerBlock)) * 2 * (C + Cg) * sizeof(double);
+}
+
 extern "C" int vqgnn_vq_moments(const float* x, int64_t ldx, const float* g, int64_t ldg, int64_t B, int C,
-                                int Cg, double* sums, void* stream) {
-  VQ_CHECK_ARG(x && sums && B > 0 && C > 0, "vq_moments: bad arguments");
+                                int Cg, double* sums, void* ws, void* stream) {
+  VQ_CHECK_ARG(x && sums && ws && B > 0 && C > 0, "vq_moments: bad arguments");
   if (!g) Cg = 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  VQ_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (C + Cg), s));
   const int tilesC = ceil_div(C, 32), tilesG = ceil_div(Cg, 32);
-  dim3 grid(ceil_div(B, kMomRowsPerBlock), tilesC + tilesG), block(32, 8);
-  vq_moments_kernel<<<grid, block, 0, s>>>(x, ldx, g, ldg, B, C, Cg, tilesC, sums);
+  const int tilesR = ceil_div(B, kMomRowsPerBlock);
+  dim3 grid(tilesR, tilesC + tilesG), block(32, 8);
+  double* part = static_cast<double*>(ws);
+  vq_moments_kernel<<<grid, block, 0, s>>>(x, ldx, g, ldg, B, C, Cg, tilesC, part);
+  VQ_LAUNCH_CHECK();
+  const int n = 2 * (C + Cg);
+  vq_moments_reduce_kernel<<<ceil_div(n, 128), 128, 0, s>>>(part, tilesR, n, sums);
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }
@@ -306,15 +335,15 @@ extern "C" int vqgnn_vq_moments(const float* x, int64_t ldx, const float* g, int
 extern "C" int vqgnn_vq_whiten(const double* sums, double count, const double* d_count, int nb, int D, int Dg, int has_grad,
                                float* run_mean_f, float* run_var_f, float* run_mean_g, float* run_var_g,
                                float eps_f, float mom_f, float eps_g, float mom_g, float grad_scale0,
-                               float grad_scale1, int training, int seed_running, int64_t* nbt_f,
-                               int64_t* nbt_g, float* scale, float* shift, void* stream) {
+                               float grad_scale1, int training, int seed_running, const int32_t* seed_mask,
+                               int64_t* nbt_f, int64_t* nbt_g, float* scale, float* shift, void* stream) {
   VQ_CHECK_ARG(nb > 0 && D > 0 && scale && shift && run_mean_f && run_var_f, "vq_whiten: bad arguments");
   VQ_CHECK_ARG(!has_grad || (run_mean_g && run_var_g && (Dg == D || Dg == D + 1)), "vq_whiten: bad grad args");
-  VQ_CHECK_ARG(!training || sums, "vq_whiten: training needs moments");
+  VQ_CHECK_ARG(!(training || seed_running || seed_mask) || sums, "vq_whiten: training / seeding needs moments");
   const int Ctot = nb * D + (has_grad ? nb * Dg : 0);
   vq_whiten_kernel<<<ceil_div(Ctot, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       sums, count, d_count, nb, D, Dg, has_grad, run_mean_f, run_var_f, run_mean_g, run_var_g, eps_f, mom_f, eps_g,
-      mom_g, grad_scale0, grad_scale1, training, seed_running, nbt_f, nbt_g, scale, shift);
+      mom_g, grad_scale0, grad_scale1, training, seed_running, seed_mask, nbt_f, nbt_g, scale, shift);
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }

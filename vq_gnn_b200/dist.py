@@ -67,15 +67,42 @@ def allreduce_mean_grads_(params: Iterable[Tensor], group=None) -> None:
         off += g.numel()
 
 
-def allgather_code_updates(batch_idx: Tensor, new_codes: Tensor, group=None):
+def allgather_code_updates(batch_idx: Tensor, new_codes: Tensor, group=None, capacity=None):
     """All-gather, in rank order, every rank's (re-assigned node ids [B], their new codes [B, nbc]) ->
-    (gidx [world * B], gcodes [world * B, nbc]), or None for a single process."""
+    (gidx [world * cap], gcodes [world * cap, nbc]), or None for a single process.
+
+    Ranks sample from their own node ranges, so their batch sizes may differ (last / partial batches, uneven
+    N / world_size).  `capacity` (>= every rank's B) fixes the per-rank slot size: shorter batches are padded
+    with node id -1, which the apply step skips.  With capacity=None every rank must bring the SAME B; that is
+    verified with one small allreduce (skipped under CUDA-graph capture, where shapes are frozen and the eager
+    warm-up of the same step has already checked them) instead of letting NCCL hang or mis-align the pairs."""
     rank, ws = world(group)
     if ws == 1:
         return None
     B, nbc = new_codes.shape
-    gidx = torch.empty(ws * B, dtype=batch_idx.dtype, device=batch_idx.device)
-    gcodes = torch.empty(ws * B, nbc, dtype=new_codes.dtype, device=new_codes.device)
+    dev = new_codes.device
+    if capacity is None:
+        capturing = dev.type == 'cuda' and torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            chk = torch.tensor([B, -B], dtype=torch.int64, device=dev)
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX, group=group)
+            hi, lo = int(chk[0]), -int(chk[1])
+            if hi != lo:
+                raise ValueError(f"allgather_code_updates: ranks bring different batch sizes ({lo}..{hi}); set "
+                                 f"VQBank.gather_capacity to the largest one")
+        cap = B
+    else:
+        cap = int(capacity)
+        if B > cap:
+            raise ValueError(f"allgather_code_updates: batch of {B} rows exceeds gather_capacity={cap}")
+    if cap != B:
+        pidx = torch.full((cap,), -1, dtype=batch_idx.dtype, device=dev)
+        pidx[:B] = batch_idx
+        pcodes = torch.zeros(cap, nbc, dtype=new_codes.dtype, device=dev)
+        pcodes[:B] = new_codes
+        batch_idx, new_codes = pidx, pcodes
+    gidx = torch.empty(ws * cap, dtype=batch_idx.dtype, device=dev)
+    gcodes = torch.empty(ws * cap, nbc, dtype=new_codes.dtype, device=dev)
     # codes travel as raw bytes: int16 is not a collective dtype on every backend
     _timed("nccl_allgather_codes", lambda: (
         dist.all_gather_into_tensor(gidx, batch_idx.contiguous(), group=group),
@@ -87,6 +114,8 @@ def apply_code_updates_(codes: Tensor, gidx: Tensor, gcodes: Tensor, k0: int = 0
     """Plain-torch application of gathered updates, LAST entry wins for a repeated node (so a node shared by two
     ranks' batches resolves identically on every replica).  The CUDA path uses vqgnn_codes_apply_updates; this is
     its device-agnostic restatement (CPU tests, fallback for odd dtypes)."""
+    keep = gidx >= 0                       # -1 = padding of a short batch (allgather_code_updates capacity)
+    gidx, gcodes = gidx[keep], gcodes[keep]
     n, nbc = gcodes.shape
     owner = torch.full((codes.shape[0],), -1, dtype=torch.long, device=codes.device)
     owner.scatter_reduce_(0, gidx.long(), torch.arange(n, device=codes.device), reduce='amax')
@@ -94,9 +123,10 @@ def apply_code_updates_(codes: Tensor, gidx: Tensor, gcodes: Tensor, k0: int = 0
     codes[gidx[win].long(), k0:k0 + nbc] = gcodes[win]
 
 
-def allgather_code_updates_(codes: Tensor, batch_idx: Tensor, new_codes: Tensor, k0: int = 0, group=None):
+def allgather_code_updates_(codes: Tensor, batch_idx: Tensor, new_codes: Tensor, k0: int = 0, group=None,
+                            capacity=None):
     """Gather + apply (see the two functions above).  Returns the gathered node ids or None when single."""
-    got = allgather_code_updates(batch_idx, new_codes, group)
+    got = allgather_code_updates(batch_idx, new_codes, group, capacity)
     if got is None:
         return None
     apply_code_updates_(codes, got[0], got[1], k0)

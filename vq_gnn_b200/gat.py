@@ -26,9 +26,13 @@ class VQGATFunction(torch.autograd.Function):
         bank = layer.bank
         B, C = x.shape
         R, dev = plan.R, x.device
+        # scores cover ALL B + B' nodes of x_input in both modes: the eval plan keeps only the batch ROWS (R = B)
+        # but its columns still reach the out-of-batch nodes, and Trick 1's max runs over every row of x_input
+        # (vq_gnn_v2/convs.py:188-211)
+        Rs = B + plan.T
         al, ar = att_l.detach().reshape(-1).contiguous(), att_r.detach().reshape(-1).contiguous()
         assert al.numel() == C + 1 and ar.numel() == C + 1
-        a_l, a_r = torch.empty(R, device=dev), torch.empty(R, device=dev)
+        a_l, a_r = torch.empty(Rs, device=dev), torch.empty(Rs, device=dev)
         stat = torch.empty(2, device=dev)
         tail_feat = tail_grad = None
         auto = plan.nnz >= 4 * max(plan.T, 1)
@@ -42,7 +46,7 @@ class VQGATFunction(torch.autograd.Function):
                 bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, st))
         ctx.tail = (tail_feat, tail_grad)
         _lib.check(lib.vqgnn_gat_scores(
-            R, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O),
+            Rs, B, _lib.ptr(x), x.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O),
             bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C, _lib.ptr(al), _lib.ptr(ar), _lib.ptr(a_l),
             _lib.ptr(a_r), _lib.ptr(stat), st))
         y = torch.empty(B, C, device=dev)

@@ -297,18 +297,6 @@ def plan_from_v2(batch_A, conv_type: str, N: int, training: bool, device) -> Bat
                      bptr, bcol, bval, beid, training)
 
 
-_PINNED_COUNTS = []      # small ring of pinned int32 scalars for deferred device->host count reads
-
-
-def _pinned_count():
-    if len(_PINNED_COUNTS) < 64:
-        _PINNED_COUNTS.append(torch.empty(1, dtype=torch.int32).pin_memory())
-        return _PINNED_COUNTS[-1]
-    t = _PINNED_COUNTS.pop(0)
-    _PINNED_COUNTS.append(t)
-    return t
-
-
 def plan_from_v2_device(batch_A, conv_type: str, N: int, device) -> BatchPlan:
     """Training-mode `plan_from_v2` with the transposed CSR built on the device (csrc/plan.cu:
     vqgnn_csr_transpose_lt) and NO host synchronisation: the number of transposed entries is copied to pinned host
@@ -328,11 +316,11 @@ def plan_from_v2_device(batch_A, conv_type: str, N: int, device) -> BatchPlan:
     brow = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     bval = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
-    ws = torch.empty(int(lib.vqgnn_csr_transpose_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(lib.vqgnn_csr_transpose_workspace_bytes(B, nnz)), dtype=torch.uint8, device=dev)
     _lib.check(lib.vqgnn_csr_transpose_lt(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), dim, nnz, B,
                                           _lib.ptr(browptr), _lib.ptr(brow), _lib.ptr(bval), _lib.ptr(count),
                                           _lib.ptr(ws), st))
-    host_count = _pinned_count()
+    host_count = torch.empty(1, dtype=torch.int32).pin_memory()    # owned by this plan (kept alive by the closure)
     host_count.copy_(count, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
@@ -395,7 +383,7 @@ def plan_from_v1_device(batch_A, conv_type: str, N: int, training: bool, device)
     tptr, tnode, tval, trval, tcount, tcr = i32(B + 1), i32(nnz), f32(nnz), f32(nnz), i32(1), i32(n_tc)
     iptr, icol, ival, icr = i32(B + 1), i32(nin), f32(nin), i32(n_ic)
     bptr, brow, bval, bcr = i32(B + 1), i32(nin), f32(nin), i32(n_ic)
-    ws = torch.empty(int(lib.vqgnn_plan_v1_workspace_bytes(N, B)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(lib.vqgnn_plan_v1_workspace_bytes(N, B, nnz, nin)), dtype=torch.uint8, device=dev)
     _lib.check(lib.vqgnn_plan_v1_build(
         _lib.ptr(r), _lib.ptr(c), _lib.ptr(v), _lib.ptr(rv), nnz, _lib.ptr(br), _lib.ptr(bc), _lib.ptr(bv), nbb,
         _lib.ptr(bidx), _lib.ptr(dinv), B, N, sym, loops, TAIL_CHUNK, ichunk,

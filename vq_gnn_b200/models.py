@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib
-from .convs import OurGATConv, OurGCNConv, Transformer  # noqa: F401
+from .convs import OurGATConv, OurGCNConv
 from .graph import MP_CHUNK, TAIL_CHUNK, TAIL_MIN_AVG_DEGREE, BatchPlan, CSRAdj, build_plan
 from .vq import VectorQuantizerEMA, VQBank
 
@@ -44,8 +44,10 @@ def _trigger(dev) -> Tensor:
     return t
 
 
-def _mp_ws(dev) -> Tensor:
-    return torch.empty(8, dtype=torch.float64, device=dev)
+def _mp_ws(dev, nnz: int, chunk: int, C: int) -> Tensor:
+    """Scratch of vqgnn_mp_fwd / vqgnn_mp_bwd: ordered info partials + the piece buffers of rows cut >= 2 times."""
+    return torch.empty(int(_lib.load().vqgnn_mp_workspace_bytes(int(nnz), int(chunk), int(C))), dtype=torch.uint8,
+                       device=dev)
 
 
 class VQConvFunction(torch.autograd.Function):
@@ -72,7 +74,6 @@ class VQConvFunction(torch.autograd.Function):
         info = torch.zeros((), device=dev)
         v1 = plan.version == 'v1'
         gq = torch.empty(B, C, device=dev) if (v1 and plan.has_rval) else None
-        ws = _mp_ws(dev) if need_info else None
         codes_g = None
         if v1 and gq is not None and layer.use_tail_kernel and (
                 layer.use_tail_kernel == 'force' or plan.nnz >= TAIL_MIN_AVG_DEGREE * B):
@@ -87,8 +88,10 @@ class VQConvFunction(torch.autograd.Function):
             _lib.check(lib.vqgnn_mp_fwd(
                 _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), None, _lib.ptr(icr), plan.small_chunk, innz, B, B,
                 _lib.ptr(x), x.stride(0), None, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
-                bank.Wp, None, 0, 1.0, 1.0, _lib.ptr(y), y.stride(0), None, 0, None, None, st))
-            gq.zero_()
+                bank.Wp, None, 0, 1.0, 1.0, _lib.ptr(y), y.stride(0), None, 0, None,
+                _lib.ptr(_mp_ws(dev, innz, plan.small_chunk, C)), st))
+            ws = torch.empty(int(lib.vqgnn_mp_fwd_tail_workspace_bytes(tnnz, TAIL_CHUNK, B, C)), dtype=torch.uint8,
+                             device=dev)
             _lib.check(lib.vqgnn_mp_fwd_tail(
                 _lib.ptr(tptr), _lib.ptr(tnode), _lib.ptr(tval), _lib.ptr(trval), _lib.ptr(tcr), TAIL_CHUNK, tnnz,
                 _lib.ptr(tcount), B, _lib.ptr(x), x.stride(0), _lib.ptr(codes_g), codes_g.shape[1], _lib.ptr(bank.O), bank.nb,
@@ -114,7 +117,7 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C,
                 float(wu) if v1 else 1.0, float(wu),
                 _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
-                _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+                _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
         ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook = layer, plan, float(wu), fire_hook
         if not hasattr(ctx, 'tail_grad'):
             ctx.tail_grad = None
@@ -134,12 +137,14 @@ class VQConvFunction(torch.autograd.Function):
         v1 = plan.version == 'v1'
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, C, device=x.device)
+            nnz_t = int(plan.bwd_col.numel())
             _lib.check(lib.vqgnn_mp_bwd(
                 _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
                 _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
                 dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
                 bank.M, bank.D, bank.Wp, _lib.ptr(ctx.tail_grad), C, 0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
-                wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0), st))
+                wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0),
+                _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
         if ctx.fire_hook:
             # the reference's hook(grad): vq.update(X_B, grad) ; c_indices[batch] = idx ; return grad
             bank.run(x, dy, plan.batch_idx, True)
@@ -171,7 +176,7 @@ def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Ten
         _lib.check(lib.vqgnn_mp_fwd(
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), None, _lib.ptr(chunks), MP_CHUNK, nnz,
             n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, None, 0, 1.0, 1.0,
-            _lib.ptr(y), y.stride(0), None, 0, None, None, st))
+            _lib.ptr(y), y.stride(0), None, 0, None, _lib.ptr(_mp_ws(x.device, nnz, MP_CHUNK, C)), st))
         return y
     # GAT: the fused kernels carry an implicit ones column (coefficient att[C]); a zero coefficient removes it from
     # the scores, and multiplying the normalised output back by its denominator gives the reference's plain sum
@@ -360,6 +365,7 @@ class LowRankGNNLayer(nn.Module):
         x = x.float()
         xc = x if x.is_contiguous() else x.contiguous()
         inited = self.inited
+        self.bank.poll_status()      # deferred 'Bad Init!' check of an earlier update: no stream stall
         do_init = (not inited or unlabeled) and (self.training or self.version == 'v2')
         if do_init:          # models.py:165-166 (v2) / v1 models.py:164-165: feature-only warm start
             self.bank.run(xc.detach(), None, plan.batch_idx, self.training)
@@ -429,6 +435,20 @@ class LowRankGNN(nn.Module):
         device = device or next(self.parameters()).device
         plan = build_plan(batch_A, self.conv_type, self.num_N, self.training, device)
         return plan.warm() if plan.device.type == 'cuda' else plan
+
+    def prepare_from_graph(self, graph, node_idx: Tensor, recovery_flag: bool = True) -> BatchPlan:
+        """Mini-batch plan straight from the device-resident normalised graph (`synth.Graph` / any object with
+        rowptr, col, val[, deg, deg_inv]) and the batch's node ids: the device-side equivalent of the reference's
+        loader + `prepare_batch_input` (vq_gnn_v2/dataloader.py:98-148 + utils/misc.py:57-75; v1:
+        vq_gnn_v1/utils/dataloader.py:64-86) without the int64 COO round trip through host memory -- only the
+        node ids cross PCIe."""
+        from . import sampling
+        if self.version == 'v2':
+            batch_A = sampling.k_hop_batch_v2(graph, node_idx, train_flag=self.training)
+        else:
+            batch_A = sampling.collate_batch_v1(graph, node_idx, train_flag=self.training,
+                                                recovery_flag=recovery_flag)
+        return self.prepare(batch_A, device=graph.col.device)
 
     def forward(self, batch, warm_up_rate=1, unlabeled=False):
         losses_full, info_backwards_full = 0, 0

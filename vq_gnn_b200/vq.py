@@ -48,7 +48,14 @@ class VQBank:
         self.scale = [float(grad_normalize_scale[0]), float(grad_normalize_scale[1])]
         self.warm_up_flag, self.momentum = warm_up_flag, momentum
         self.num_N = num_N
-        self.bn_inited = False
+        self.bn_inited = [False] * nb      # one flag per quantiser (vq.py:100), not per layer
+        # True (default): per-codeword statistics by the ordered segmented sum (vqgnn_vq_segsum: bit-stable results);
+        # False: float atomics fused into the assignment kernel's epilogue (order-dependent last bits)
+        self.deterministic = True
+        # multi-GPU: fixed capacity (rows) of the per-rank slot in the code-update all-gather; None = every rank must
+        # bring the same batch size, which is then verified with one small allreduce per update
+        self.gather_capacity: Optional[int] = None
+        self._status_host = None           # (pinned int32, event) of the last asynchronous status read
         # 0: exact-fp32 SIMT kernel (default: bit-stable codes, the parity anchor), 1: tcgen05 3xTF32 kernel,
         # 'auto': tcgen05 when it is the faster one (M >= 512 and a packed width it supports; measured on B200:
         # 0.55 vs 0.45 ms at M = 256, 0.57 vs 0.89 at M = 1024, 0.62 vs 1.41 at M = 4096)
@@ -137,28 +144,38 @@ class VQBank:
         shift = torch.empty(C + Cg, device=dev)
         sums, d_count = None, None
         count = float(B)
-        if training:
+        # vq.py:216-221: the FIRST update() of a quantiser seeds both BatchNorms' running statistics from the batch
+        # (whatever the mode); feature_update never does
+        seeds = [joint and not self.bn_inited[k] for k in range(k0, k0 + nbc)]
+        seed, seed_mask = (1 if seeds[0] else 0), None
+        if any(seeds) and not all(seeds):
+            seed_mask = torch.tensor([int(v) for v in seeds], dtype=torch.int32, device=dev)
+        if training or any(seeds):
             sums = torch.empty(2 * (C + Cg) + 1, dtype=torch.float64, device=dev)
+            mws = torch.empty(int(lib.vqgnn_vq_moments_workspace_bytes(B, C, Cg)) // 8 + 1, dtype=torch.float64,
+                              device=dev)
             _lib.check(lib.vqgnn_vq_moments(_lib.ptr(xk), xk.stride(0), _lib.ptr(gk),
-                                            gk.stride(0) if joint else 0, B, C, Cg, _lib.ptr(sums), st))
+                                            gk.stride(0) if joint else 0, B, C, Cg, _lib.ptr(sums), _lib.ptr(mws), st))
             if self.distributed:   # global batch statistics: every rank whitens identically
                 sums[-1:].fill_(float(B))          # a fill kernel (capturable), not a host copy
                 dist.allreduce_sum_(sums, self.process_group)
                 d_count = sums[-1:]
-        seed = 1 if (joint and training and not self.bn_inited) else 0
         _lib.check(lib.vqgnn_vq_whiten(
             _lib.ptr(sums), count, _lib.ptr(d_count), nbc, D, Dg, 1 if joint else 0, _lib.ptr(rm_f), _lib.ptr(rv_f),
             _lib.ptr(rm_g) if joint else None, _lib.ptr(rv_g) if joint else None,
             1e-5, 0.1, self.eps, self.momentum, self.scale[0], self.scale[1], 1 if training else 0, seed,
-            _lib.ptr(nbt_f) if training else None, _lib.ptr(nbt_g) if (training and joint) else None,
-            _lib.ptr(scale), _lib.ptr(shift), st))
-        if joint and training:
-            self.bn_inited = True
+            _lib.ptr(seed_mask), _lib.ptr(nbt_f) if training else None,
+            _lib.ptr(nbt_g) if (training and joint) else None, _lib.ptr(scale), _lib.ptr(shift), st))
+        if joint:
+            for k in range(k0, k0 + nbc):
+                self.bn_inited[k] = True
         idx = torch.empty(B, nbc, dtype=torch.int16, device=dev)
         stats = None
+        fused_stats = training and not self.deterministic
         if training:
             stats = torch.empty(nbc, M, self.Ws, device=dev)
-            _lib.check(lib.vqgnn_fill_zero(_lib.ptr(stats), stats.numel() * 4, st))
+            if fused_stats:
+                _lib.check(lib.vqgnn_fill_zero(_lib.ptr(stats), stats.numel() * 4, st))
         codes_ptr, bidx = None, None
         if write_codes and batch_idx is not None:
             assert batch_idx.dtype == torch.int32 and batch_idx.is_cuda
@@ -174,8 +191,14 @@ class VQBank:
         _lib.check(lib.vqgnn_vq_assign(
             _lib.ptr(xk), xk.stride(0), _lib.ptr(gk), gk.stride(0) if joint else 0, _lib.ptr(scale),
             _lib.ptr(shift), _lib.ptr(E), B, nbc, M, D, Dg, Wp, _lib.ptr(bidx), codes_ptr, self.nb,
-            _lib.ptr(idx), _lib.ptr(stats), int(impl), _lib.ptr(ws), ws_bytes, st))
+            _lib.ptr(idx), _lib.ptr(stats) if fused_stats else None, int(impl), _lib.ptr(ws), ws_bytes, st))
         if training:
+            if not fused_stats:    # ordered segmented sum over the assignments: no float atomics
+                sb = int(lib.vqgnn_vq_segsum_workspace_bytes(B, nbc, M))
+                sws = torch.empty(sb, dtype=torch.uint8, device=dev)
+                _lib.check(lib.vqgnn_vq_segsum(
+                    _lib.ptr(xk), xk.stride(0), _lib.ptr(gk), gk.stride(0) if joint else 0, _lib.ptr(scale),
+                    _lib.ptr(shift), _lib.ptr(idx), B, nbc, M, D, Dg, Wp, _lib.ptr(stats), _lib.ptr(sws), sb, st))
             if self.distributed:
                 dist.allreduce_sum_(stats, self.process_group)
             _lib.check(lib.vqgnn_vq_finalize(
@@ -187,7 +210,7 @@ class VQBank:
             # every replica of the code table learns the other ranks' re-assignments (their batch nodes are this
             # rank's out-of-batch neighbours): one all-gather of (node id, codes) per update, applied by one kernel
             # with last-entry-wins semantics (identical on every rank)
-            got = dist.allgather_code_updates(bidx, idx, self.process_group)
+            got = dist.allgather_code_updates(bidx, idx, self.process_group, capacity=self.gather_capacity)
             if got is not None:
                 gidx, gcodes = got
                 if self._owner_ws is None or self._owner_ws.device != dev:
@@ -208,10 +231,32 @@ class VQBank:
         return idx
 
     def check_status(self):
-        """Lazy 'Bad Init!' check (vq.py:188-189, 253-254): one host sync."""
+        """'Bad Init!' check (vq.py:188-189, 253-254): one host sync."""
         if self.status.is_cuda and int(self.status.item()) & 1:
             self.status.zero_()
+            self._status_host = None
             raise ValueError('Bad Init!')
+
+    def poll_status(self):
+        """The same check without stalling the stream: reads the status word that was copied to pinned memory after
+        an EARLIER update (raising one or two steps late), then queues the next copy.  Called by the layers on every
+        forward, so a bad initialisation surfaces by itself; skipped during CUDA-graph capture."""
+        if not self.status.is_cuda or torch.cuda.is_current_stream_capturing():
+            return
+        if self._status_host is not None:
+            host, ev = self._status_host
+            if not ev.query():
+                return
+            if int(host[0]) & 1:
+                self.status.zero_()
+                self._status_host = None
+                raise ValueError('Bad Init!')
+        else:
+            host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        host.copy_(self.status, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._status_host = (host, ev)
 
 
 class VectorQuantizerEMA(nn.Module):
@@ -264,15 +309,17 @@ class VectorQuantizerEMA(nn.Module):
 
     @property
     def bn_inited(self) -> bool:
-        return self._bank.bn_inited
+        return self._bank.bn_inited[self._branch]
 
     @bn_inited.setter
     def bn_inited(self, v: bool):
-        self._bank.bn_inited = bool(v)
+        self._bank.bn_inited[self._branch] = bool(v)
 
     def _pull_into_bank(self, bank: VQBank, i: int):
         """Copy this module's (possibly just-moved / just-loaded) buffers into slot i of `bank`."""
         W = bank.W
+        if bank is not self._bank:
+            bank.bn_inited[i] = self._bank.bn_inited[self._branch]
         bank.E[i, :, :W] = self._embedding
         bank.O[i, :, :W] = self._embedding_output
         bank.Wm[i, :, :W] = self._ema_w
