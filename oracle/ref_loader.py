@@ -13,7 +13,19 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("VQGNN_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _default_root() -> str:
+    """/root/reference in the builder container; on the GPU box the git-ignored copy `oracle/_ref/` that
+    `make oracle_ref` made there (it travels with the gpurun snapshot like the built .so)."""
+    for p in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(p, "vq_gnn_v2", "vq.py")):
+            return p
+    return "/root/reference"
+
+
+REF_ROOT = os.environ.get("VQGNN_REFERENCE_ROOT") or _default_root()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 _CACHE = {}
 _SHADOWED = ("vq", "convs", "models", "utils", "dataloader", "models_inductive")

@@ -59,10 +59,12 @@ def random_edges(N: int, num_undirected: int, seed: int = 0, power_law: float = 
     E = int(num_undirected)
     if power_law > 0:
         u = torch.rand(N, generator=g, device=device).clamp_(min=1e-6)
-        w = u.pow(-1.0 / power_law)
-        cdf = torch.cumsum(w / w.sum(), 0)
-        src = torch.searchsorted(cdf, torch.rand(E, generator=g, device=device)).clamp_(max=N - 1)
-        dst = torch.searchsorted(cdf, torch.rand(E, generator=g, device=device)).clamp_(max=N - 1)
+        # the CDF is accumulated in fp64 on the HOST: a parallel fp32 prefix sum on the GPU is not reproducible from
+        # process to process, and every rank (and both bench arms) must build the SAME graph
+        w = u.double().cpu().pow(-1.0 / power_law)
+        cdf = torch.cumsum(w / w.sum(), 0).to(device)
+        src = torch.searchsorted(cdf, torch.rand(E, generator=g, device=device).double()).clamp_(max=N - 1)
+        dst = torch.searchsorted(cdf, torch.rand(E, generator=g, device=device).double()).clamp_(max=N - 1)
     else:
         src = torch.randint(0, N, (E,), generator=g, device=device)
         dst = torch.randint(0, N, (E,), generator=g, device=device)
