@@ -249,6 +249,39 @@ int vqgnn_csr_transpose_lt(const int32_t* rowptr, const int32_t* col, const floa
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Mini-batch graph construction on the device from the RESIDENT normalised graph (CSR: rowptr int64 [N+1],
+ * col int32 [nnz], val fp32 [nnz]) and the batch's node ids (int64 [B]) -- SURVEY.md section 8 f1.  Only the node
+ * ids cross PCIe; the reference builds the batch graph on the CPU and ships an int64 COO (vq_gnn_v2/utils/misc.py:57-75).
+ * All calls of one batch share one workspace of vqgnn_khop_workspace_bytes(N, N) bytes (it holds the node -> row table).
+ *
+ * v2, `_k_hop_subgraph` (vq_gnn_v2/dataloader.py:98-148): subset = [batch nodes ; out-of-batch 1-hop neighbours B',
+ * ascending node id]; train keeps every edge inside the subset (R = B + B' rows), eval only the batch rows (R = B).
+ *   vqgnn_khop_mark : batch_idx32 [B] (the ids as int32), tail_node [capacity N; first *T valid], *T = B'
+ *   vqgnn_khop_count: out_rowptr [R+1] of the relabelled CSR, *nnz = its entry count      (after the host read T)
+ *   vqgnn_khop_fill : out_col / out_val [nnz]; column ids < B = batch rows, >= B = tail entry (col - B); inside a
+ *                     row the graph's stored order is kept (stable compaction)               (after the host read nnz)
+ * v1, `__collate__` (vq_gnn_v1/utils/dataloader.py:64-86): the reference's own batch tuple in its own format
+ * (int64 COO, row-sorted), i.e. exactly what vqgnn_plan_v1_build consumes:
+ *   vqgnn_collate_v1_count: off_bn / off_bb [B+1] (row offsets of A_BN / A_BB), counts[0] = nnz(A_BN),
+ *                           counts[1] = nnz(A_BB) (with_bb == 0: A_BB is not built, counts[1] = 0)
+ *   vqgnn_collate_v1_fill : A_BN (bn_r, bn_c, bn_v), nb_v = A_NB_v = deg[row node] * v * deg_inv[col] (NULL: skip),
+ *                           A_BB (bb_r, bb_c local ids, bb_v; NULL: skip), deg_inv_out [B] = deg_inv[batch nodes]. */
+size_t vqgnn_khop_workspace_bytes(int64_t N, int64_t rows);
+int vqgnn_khop_mark(const int64_t* rowptr, const int32_t* col, const int64_t* node_idx, int64_t B, int64_t N,
+                    int32_t* batch_idx32, int32_t* tail_node, int32_t* T, void* ws, void* stream);
+int vqgnn_khop_count(const int64_t* rowptr, const int32_t* col, const int64_t* node_idx, const int32_t* tail_node,
+                     int64_t B, int64_t R, int64_t N, int32_t* out_rowptr, int32_t* nnz, void* ws, void* stream);
+int vqgnn_khop_fill(const int64_t* rowptr, const int32_t* col, const float* val, const int64_t* node_idx,
+                    const int32_t* tail_node, int64_t B, int64_t R, int64_t N, const int32_t* out_rowptr,
+                    int32_t* out_col, float* out_val, void* ws, void* stream);
+int vqgnn_collate_v1_count(const int64_t* rowptr, const int32_t* col, const int64_t* node_idx, int64_t B, int64_t N,
+                           int with_bb, int32_t* off_bn, int32_t* off_bb, int32_t* counts, void* ws, void* stream);
+int vqgnn_collate_v1_fill(const int64_t* rowptr, const int32_t* col, const float* val, const float* gdeg,
+                          const float* gdeg_inv, const int64_t* node_idx, int64_t B, int64_t N, const int32_t* off_bn,
+                          const int32_t* off_bb, int64_t* bn_r, int64_t* bn_c, float* bn_v, float* nb_v, int64_t* bb_r,
+                          int64_t* bb_c, float* bb_v, float* deg_inv_out, void* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Message passing, GAT, v2 ("B+B'") formulation: OurGATConv.forward/message (vq_gnn_v2/convs.py:165-266)
  * with vq_softmax == un-normalised exp (vq_gnn_v2/utils/vq_softmax.py:41-57), fused with the codeword
  * gather, the ones-column denominator and the batch-row normalisation of vq_gnn_v2/models.py:161-198.

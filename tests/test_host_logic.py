@@ -106,3 +106,33 @@ def test_plan_v2_roundtrip(train):
     assert torch.equal(plan.tail_node.long(), subset[B:])
     # batch nodes lead the subset (vq_gnn_v2/dataloader.py:128)
     assert torch.equal(subset[:B], batch_idx)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_k_hop_batch_matches_the_reference_loader(train):
+    """sampling.k_hop_batch_v2 (the device-agnostic restatement that csrc/khop.cu is checked against on the GPU) vs the
+    UNMODIFIED reference's `OurDataLoader._k_hop_subgraph` (vq_gnn_v2/dataloader.py:98-148) run through
+    oracle/ref_loader: same subset (batch nodes first), same edges and values in global node ids."""
+    import types
+    from oracle import ref_loader
+    from vq_gnn_b200 import sampling
+    if not ref_loader.available():
+        pytest.skip("reference sources not on this box")
+    ref = ref_loader.load_reference("v2")
+    N, B = 500, 90
+    g = H.make_graph(N, 4000, "GCN", "v2", seed=41, power_law=1.4)
+    nodes = torch.randperm(N, generator=torch.Generator().manual_seed(3))[:B]
+    fake = types.SimpleNamespace(N=N, edge_index=torch.stack([g.row, g.col]), edge_w=g.val, train_flag=train)
+    subset_r, ei_r, w_r = ref.dataloader.OurDataLoader._k_hop_subgraph(fake, nodes)
+    batch_idx, subset, adj = sampling.k_hop_batch_v2(g, nodes, train_flag=train)
+    assert torch.equal(subset[:B], nodes) and torch.equal(subset_r[:B], nodes)
+    assert torch.equal(torch.sort(subset)[0], torch.sort(subset_r)[0])
+
+    def triples(sub, row, col, val):
+        key = sub[row] * N + sub[col]
+        order = torch.argsort(key)
+        return key[order], val[order]
+    row, col, val = adj.coo()
+    k0, v0 = triples(subset, row, col, val)
+    k1, v1 = triples(subset_r, ei_r[0], ei_r[1], w_r)
+    assert torch.equal(k0, k1) and torch.equal(v0, v1)

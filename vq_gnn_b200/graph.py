@@ -480,6 +480,113 @@ def plan_from_v1(batch_A, conv_type: str, N: int, training: bool, device) -> Bat
                      nnz=nnz, has_rval=True)
 
 
+def _pinned_i32(n: int = 1) -> Tensor:
+    return torch.empty(n, dtype=torch.int32).pin_memory()
+
+
+def plan_from_graph_v2(g, node_idx: Tensor, conv_type: str, training: bool = True) -> BatchPlan:
+    """v2 batch plan straight from the device-resident graph `g` (rowptr int64, col / col32, val) and the batch's
+    node ids: csrc/khop.cu restates `_k_hop_subgraph` + `prepare_batch_input` (vq_gnn_v2/dataloader.py:98-148,
+    utils/misc.py:57-75) on the device -- subset = [batch ; ascending out-of-batch 1-hop neighbours], train keeps
+    every edge inside the subset, eval the batch rows only -- and hands the relabelled int32 CSR to the kernels
+    without ever forming the reference's int64 COO.  Two small device->host reads (B' and nnz) size the outputs."""
+    from . import _lib
+    lib, st = _lib.load(), _lib.stream()
+    dev = g.col.device
+    N = int(g.N)
+    ids = node_idx.to(dev).long().contiguous()
+    _lib.require_device(g.val)
+    B = int(ids.numel())
+    rowptr, col, val = g.rowptr.contiguous(), g.col32, g.val.contiguous()
+    ws = torch.empty(int(lib.vqgnn_khop_workspace_bytes(N, N)), dtype=torch.uint8, device=dev)
+    bidx = torch.empty(B, dtype=torch.int32, device=dev)
+    tail_all = torch.empty(N, dtype=torch.int32, device=dev)
+    cnt = torch.empty(2, dtype=torch.int32, device=dev)
+    _lib.check(lib.vqgnn_khop_mark(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(ids), B, N, _lib.ptr(bidx),
+                                   _lib.ptr(tail_all), _lib.ptr(cnt), _lib.ptr(ws), st))
+    host = _pinned_i32(2)
+    host[:1].copy_(cnt[:1], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    T = int(host[0])
+    tail_node = tail_all[:T]
+    R = B + T if training else B
+    out_rowptr = torch.empty(R + 1, dtype=torch.int32, device=dev)
+    _lib.check(lib.vqgnn_khop_count(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(ids), _lib.ptr(tail_node), B, R, N,
+                                    _lib.ptr(out_rowptr), _lib.ptr(cnt[1:]), _lib.ptr(ws), st))
+    host[1:].copy_(cnt[1:], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    nnz = int(host[1])
+    out_col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    out_val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    _lib.check(lib.vqgnn_khop_fill(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(ids), _lib.ptr(tail_node),
+                                   B, R, N, _lib.ptr(out_rowptr), _lib.ptr(out_col), _lib.ptr(out_val), _lib.ptr(ws),
+                                   st))
+    out_col, out_val = out_col[:nnz], out_val[:nnz]
+    # transposed CSR over the batch columns (backward structure), entry count read lazily
+    browptr = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    brow = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    bval = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    tws = torch.empty(int(lib.vqgnn_csr_transpose_workspace_bytes(B, nnz)), dtype=torch.uint8, device=dev)
+    _lib.check(lib.vqgnn_csr_transpose_lt(_lib.ptr(out_rowptr), _lib.ptr(out_col), _lib.ptr(out_val), R, nnz, B,
+                                          _lib.ptr(browptr), _lib.ptr(brow), _lib.ptr(bval), _lib.ptr(count),
+                                          _lib.ptr(tws), st))
+    host_count = _pinned_i32(1)
+    host_count.copy_(count, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+
+    def bwd():
+        ev.synchronize()
+        n = int(host_count[0])
+        return browptr, brow[:n], bval[:n]
+
+    return BatchPlan('v2', conv_type, B, R, T, N, bidx, out_rowptr, out_col, out_val, None, tail_node, None, None,
+                     None, None, training, extras={'_keep': (ws, tws, count, brow, bval, browptr, tail_all, ids)},
+                     bwd_builder=bwd)
+
+
+def batch_from_graph_v1(g, node_idx: Tensor, train_flag: bool = True, recovery_flag: bool = True):
+    """The reference's v1 batch tuple (deg_inv[B], A_BN (r, c, v), A_BB (r, c, v) | None, A_NB_v | None, batch_idx)
+    (vq_gnn_v1/utils/dataloader.py:64-86) assembled on the device from the resident graph (csrc/khop.cu), in the
+    reference's own COO format: what `mapper` / vqgnn_plan_v1_build consume.  One device->host read (the two
+    entry counts)."""
+    from . import _lib
+    lib, st = _lib.load(), _lib.stream()
+    dev = g.col.device
+    N = int(g.N)
+    ids = node_idx.to(dev).long().contiguous()
+    _lib.require_device(g.val)
+    B = int(ids.numel())
+    rowptr, col, val = g.rowptr.contiguous(), g.col32, g.val.contiguous()
+    with_bb = bool(recovery_flag and train_flag)
+    with_nb = bool(g.conv_type != 'GCN' and train_flag)
+    ws = torch.empty(int(lib.vqgnn_khop_workspace_bytes(N, N)), dtype=torch.uint8, device=dev)
+    off_bn = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    off_bb = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    cnt = torch.empty(2, dtype=torch.int32, device=dev)
+    _lib.check(lib.vqgnn_collate_v1_count(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(ids), B, N, int(with_bb),
+                                          _lib.ptr(off_bn), _lib.ptr(off_bb), _lib.ptr(cnt), _lib.ptr(ws), st))
+    host = _pinned_i32(2)
+    host.copy_(cnt, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    nnz, nbb = int(host[0]), int(host[1])
+    i64 = lambda n: torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    f32 = lambda n: torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    bn_r, bn_c, bn_v = i64(nnz), i64(nnz), f32(nnz)
+    nb_v = f32(nnz) if with_nb else None
+    bb = (i64(nbb), i64(nbb), f32(nbb)) if with_bb else (None, None, None)
+    deg_inv = f32(B)
+    _lib.check(lib.vqgnn_collate_v1_fill(
+        _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(g.deg), _lib.ptr(g.deg_inv), _lib.ptr(ids), B, N,
+        _lib.ptr(off_bn), _lib.ptr(off_bb), _lib.ptr(bn_r), _lib.ptr(bn_c), _lib.ptr(bn_v), _lib.ptr(nb_v),
+        _lib.ptr(bb[0]), _lib.ptr(bb[1]), _lib.ptr(bb[2]), _lib.ptr(deg_inv), _lib.ptr(ws), st))
+    A_BN = (bn_r[:nnz], bn_c[:nnz], bn_v[:nnz])
+    A_BB = (bb[0][:nbb], bb[1][:nbb], bb[2][:nbb]) if with_bb else None
+    A_NB_v = nb_v[:nnz] if with_nb else None
+    return deg_inv[:B], A_BN, A_BB, A_NB_v, ids
+
+
 def build_plan(batch_A, conv_type: str, N: int, training: bool, device) -> BatchPlan:
     if isinstance(batch_A, BatchPlan):
         return batch_A

@@ -442,12 +442,11 @@ class LowRankGNN(nn.Module):
         loader + `prepare_batch_input` (vq_gnn_v2/dataloader.py:98-148 + utils/misc.py:57-75; v1:
         vq_gnn_v1/utils/dataloader.py:64-86) without the int64 COO round trip through host memory -- only the
         node ids cross PCIe."""
-        from . import sampling
+        from . import graph as G
         if self.version == 'v2':
-            batch_A = sampling.k_hop_batch_v2(graph, node_idx, train_flag=self.training)
-        else:
-            batch_A = sampling.collate_batch_v1(graph, node_idx, train_flag=self.training,
-                                                recovery_flag=recovery_flag)
+            plan = G.plan_from_graph_v2(graph, node_idx, self.conv_type, self.training)
+            return plan.warm()
+        batch_A = G.batch_from_graph_v1(graph, node_idx, train_flag=self.training, recovery_flag=recovery_flag)
         return self.prepare(batch_A, device=graph.col.device)
 
     def forward(self, batch, warm_up_rate=1, unlabeled=False):

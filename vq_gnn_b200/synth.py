@@ -34,6 +34,14 @@ class Graph:
     def nnz(self) -> int:
         return int(self.col.numel())
 
+    @property
+    def col32(self) -> Tensor:
+        """int32 mirror of `col` for the device-side batch builders (csrc/khop.cu); built once."""
+        c = self.__dict__.get('_col32')
+        if c is None or c.device != self.col.device:
+            c = self.__dict__['_col32'] = self.col.to(torch.int32)
+        return c
+
     def to(self, device) -> "Graph":
         mv = lambda t: None if t is None else t.to(device)
         return Graph(self.N, mv(self.rowptr), mv(self.row), mv(self.col), mv(self.val),
