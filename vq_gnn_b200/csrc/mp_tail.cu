@@ -1,4 +1,5 @@
 // Out-of-batch ("tail") message passing with the codebooks of a branch GROUP resident in shared memory.
+// (round 2: lane = (entry slot, branch) instead of lane = entry -- 8 accumulators per lane, 32 warps per SM.)
 //
 // The generic kernel (mp.cu) fetches one 32 B codeword sector per (entry, branch) through L1tex/L2 and is bound
 // by the L1tex wavefront rate (profiles/r1_mp_fwd_ncu_full.txt: 484 M sectors, 1.2 sectors/clk/SM).  For the v1
@@ -8,8 +9,9 @@
 //   * reads the G codes of a neighbour with ONE 16 B load from a group-major copy of the code table
 //     (codes_g [ceil(nb/G)][N][8] int16), i.e. one global sector per (entry, group) instead of G,
 //   * gathers codewords with LDS.128 (16 B chunk index XOR-swizzled so random codes spread over all banks),
-//   * maps lane = entry, accumulates lane-private partial sums for the row, and at the end of a row segment
-//     reduce-scatters the 64 partial sums across the warp (62 shuffles) into vector REDs on y / gq.
+//   * maps lane = (entry slot, branch): a warp advances 32 / G entries per sub-step, every lane gathers ITS branch's
+//     codeword of its slot's entry and keeps 8 partial sums; a row ends with 32 / G shuffles per column into the
+//     slot-0 lanes, which store / RED 16 B vectors of y and gq.
 // Work items = (branch group, block of 512-entry chunks), dealt round-robin to one persistent CTA per SM.
 //   yt[r, k*4..] = sum_e val[e] * feat_scale * O_k[code_k(node[e]), :4]
 //   gq[r, k*4..] = sum_e rval[e]            * O_k[code_k(node[e]), 4:8]
@@ -21,48 +23,18 @@
 
 namespace vqgnn {
 
-constexpr int kTailWarps = 16;
+constexpr int kTailWarps = 32;
 constexpr int kTailThreads = kTailWarps * 32;
 
-__device__ __forceinline__ void red_v2(float* p, float a, float b) {
-  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void red_v4(float* p, const float (&v)[4]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
 }
 
-// v[0..63] summed over the 32 lanes; lane L ends up with the totals of v[2L] and v[2L+1]
-__device__ __forceinline__ void warp_reduce_scatter64(float (&v)[64], int lane, float& out0, float& out1) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const bool up = lane & 16;
-    const float keep = up ? v[i + 32] : v[i], send = up ? v[i] : v[i + 32];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool up = lane & 8;
-    const float keep = up ? v[i + 16] : v[i], send = up ? v[i] : v[i + 16];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 4;
-    const float keep = up ? v[i + 8] : v[i], send = up ? v[i] : v[i + 8];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 2;
-    const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 1;
-    const float keep = up ? v[i + 2] : v[i], send = up ? v[i] : v[i + 2];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  out0 = v[0], out1 = v[1];
-}
-
+// Lane mapping: a warp works on EPS = 32 / G entries at a time; lane = slot * G + g handles branch g of the group
+// for the entry in `slot` and keeps only that branch's 8 partial sums (4 feature + 4 gradient columns) in
+// registers -- 8 accumulators per lane instead of 64 (lane = entry), which lets 32 warps share the SM and removes the
+// 62-shuffle reduce-scatter: a row ends with EPS shuffles per column into the slot-0 lanes.
 template <int G>
 __global__ void __launch_bounds__(kTailThreads, 1)
     mp_tail_smem_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ node,
@@ -72,11 +44,17 @@ __global__ void __launch_bounds__(kTailThreads, 1)
                         float feat_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ gq, int64_t ldgq,
                         float* __restrict__ py, float* __restrict__ pgq, int C, int ng, int cpi,
                         int items_per_group) {
+  constexpr int EPS = 32 / G;          // entries per sub-step (4 for G = 8, 5 for G = 6)
+  constexpr int BATCH = 32 / EPS * EPS;  // entries staged per batch (32 / 30): one per lane
   extern __shared__ __align__(128) unsigned char cb_smem[];  // [G][M] codewords of 32 B, 16 B chunks swizzled
+  __shared__ uint4 stage[kTailWarps][32];                    // per warp: the batch's code vectors (8 int16 each)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* cb_ptr = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cb_smem) + 127) & ~uintptr_t(127));
   const uint32_t cb_base = static_cast<uint32_t>(__cvta_generic_to_shared(cb_ptr));
+  const uint32_t st_base = static_cast<uint32_t>(__cvta_generic_to_shared(&stage[warp][0]));
   const int branch_bytes = M * 32;
+  const int slot = lane / G, g = lane - slot * G;
+  const bool lane_on = slot < EPS;
   __shared__ int next_chunk;  // warps of the CTA draw the item's chunks dynamically
   if (d_nnz) {  // entry count only known on the device (vqgnn_plan_v1_build): the host sized the grid by an upper bound
     nnz = __ldg(d_nnz);
@@ -107,6 +85,9 @@ __global__ void __launch_bounds__(kTailThreads, 1)
     __syncthreads();  // every warp is done with the previous item (and its chunk counter)
     if (threadIdx.x == 0) next_chunk = c_begin;
     __syncthreads();
+    const bool g_on = lane_on && g < gcount;
+    const uint32_t my_cb = cb_base + g * branch_bytes;
+    const int colbase = (kbase + g) * 4;
 
     while (true) {
       int ch = 0;
@@ -114,115 +95,124 @@ __global__ void __launch_bounds__(kTailThreads, 1)
       ch = __shfl_sync(0xffffffffu, ch, 0);
       if (ch >= c_end) break;
       const int eb = ch * chunk, ee = min(eb + chunk, nnz);
-      float acc[64];
+      float acc[8];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
       // rows: lane i holds rowptr[rbase + i]
       int r = __ldg(chunk_row + ch);
       int rbase = r;
       int rp_l = __ldg(rowptr + min(rbase + lane, B));
       int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
-      bool pending = false;
-      // emit the reduced sums of the current row segment (lane L holds columns 2L, 2L+1 of the group's 64)
-      auto emit = [&](float o0, float o1, bool whole) {
-        const int gI = lane >> 2, jj = (lane & 3) * 2;
-        if (gI >= gcount) return;
-        const int colbase = (kbase + gI) * 4 + (jj & 3);
-        const int kind = piece_kind(whole, rs, re, eb, chunk);
-        const int64_t poff = (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + colbase;
-        float* dst = jj < 4 ? y + static_cast<int64_t>(r) * ldy + colbase
-                            : (gq ? gq + static_cast<int64_t>(r) * ldgq + colbase : nullptr);
-        float* pdst = (jj < 4 ? py : pgq) + poff;
-        if (!dst) return;
-        if (kind == kPieceWhole) *reinterpret_cast<float2*>(dst) = make_float2(o0, o1);
-        else if (kind == kPieceRed) red_v2(dst, o0, o1);
-        else *reinterpret_cast<float2*>(pdst) = make_float2(o0, o1);
+
+      // the row segment [.., seg_end) is complete: sum the EPS slots of every column into the slot-0 lanes and emit
+      auto flush = [&](bool whole) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          t[i] = acc[i];
+#pragma unroll
+          for (int sI = 1; sI < EPS; ++sI) t[i] += __shfl_sync(0xffffffffu, acc[i], min(sI * G + g, 31));
+          acc[i] = 0.f;
+        }
+        if (slot == 0 && g < gcount) {
+          const int kind = piece_kind(whole, rs, re, eb, chunk);
+          const int64_t poff = (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + colbase;
+          const float tf[4] = {t[0], t[1], t[2], t[3]}, tq[4] = {t[4], t[5], t[6], t[7]};
+          float* yp = y + static_cast<int64_t>(r) * ldy + colbase;
+          if (kind == kPieceWhole) *reinterpret_cast<float4*>(yp) = make_float4(tf[0], tf[1], tf[2], tf[3]);
+          else if (kind == kPieceRed) red_v4(yp, tf);
+          else *reinterpret_cast<float4*>(py + poff) = make_float4(tf[0], tf[1], tf[2], tf[3]);
+          if (gq) {
+            float* gp = gq + static_cast<int64_t>(r) * ldgq + colbase;
+            if (kind == kPieceWhole) *reinterpret_cast<float4*>(gp) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+            else if (kind == kPieceRed) red_v4(gp, tq);
+            else *reinterpret_cast<float4*>(pgq + poff) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+          }
+        }
+      };
+      auto next_row = [&](int upto) {   // advance to the row that holds entry `upto`
+        do {
+          ++r;
+          if (r - rbase >= 31) {
+            rbase = r;
+            rp_l = __ldg(rowptr + min(rbase + lane, B));
+          }
+          rs = __shfl_sync(0xffffffffu, rp_l, r - rbase);
+          re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
+        } while (re <= upto);
       };
 
-      // software pipeline: (node, val, rval) two batches ahead, codes one batch ahead
+      // software pipeline: (node, val, rval) two batches ahead, code vectors one batch ahead
       int node_n = 0;
-      float v_n = 0.f, rv_n = 0.f;  // batch i+1
+      float v_n = 0.f, rv_n = 0.f;
       uint4 cv_n = make_uint4(0, 0, 0, 0);
       {
         const int e = eb + lane;
-        if (e < ee) node_n = __ldg(node + e), v_n = __ldg(val + e), rv_n = __ldg(rval + e);
+        if (lane < BATCH && e < ee) node_n = __ldg(node + e), v_n = __ldg(val + e), rv_n = __ldg(rval + e);
         cv_n = __ldg(reinterpret_cast<const uint4*>(cg + static_cast<int64_t>(node_n) * 8));
       }
       int node_nn = 0;
-      float v_nn = 0.f, rv_nn = 0.f;  // batch i+2
+      float v_nn = 0.f, rv_nn = 0.f;
       {
-        const int e = eb + 32 + lane;
-        if (e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
+        const int e = eb + BATCH + lane;
+        if (lane < BATCH && e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
       }
+      bool pending = false;
 
-      for (int bb = eb; bb < ee; bb += 32) {
+      for (int bb = eb; bb < ee; bb += BATCH) {
         const float v_l = v_n * feat_scale, rv_l = rv_n;
-        const uint4 cv = cv_n;
+        __syncwarp();
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st_base + lane * 16), "r"(cv_n.x), "r"(cv_n.y),
+                     "r"(cv_n.z), "r"(cv_n.w)
+                     : "memory");
+        __syncwarp();
         // advance the pipeline
         node_n = node_nn, v_n = v_nn, rv_n = rv_nn;
         cv_n = __ldg(reinterpret_cast<const uint4*>(cg + static_cast<int64_t>(node_n) * 8));
         {
-          const int e = bb + 64 + lane;
+          const int e = bb + 2 * BATCH + lane;
           node_nn = 0, v_nn = 0.f, rv_nn = 0.f;
-          if (e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
+          if (lane < BATCH && e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
         }
-        // codeword addresses of this lane's entry
-        uint32_t addr[G];   // feature chunk; the gradient chunk is the other 16 B of the same 32 B codeword
-        const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-        for (int gI = 0; gI < G; ++gI) {
-          const uint32_t code = (gI & 1) ? (cw[gI >> 1] >> 16) : (cw[gI >> 1] & 0xffffu);
-          addr[gI] = cb_base + gI * branch_bytes + code * 32 + ((code >> 2) & 1) * 16;  // cb_base is 32 B aligned
-        }
-        const int e = bb + lane;
-        const int bend = min(bb + 32, ee);
-        int j0 = bb;
-        while (j0 < bend) {  // pieces of this batch that belong to one row
-          const int pend = min(re, bend);
-          const bool on = e >= j0 && e < pend;
-          const float vf = on ? v_l : 0.f, vr = on ? rv_l : 0.f;
-#pragma unroll
-          for (int gI = 0; gI < G; ++gI) {
-            if (gI < gcount) {
-              float4 f, q;
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                           : "r"(addr[gI]));
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
-                           : "r"(addr[gI] ^ 16u));  // valid because cb_base is a multiple of 32
-              float* a = acc + gI * 8;
-              a[0] = fmaf(vf, f.x, a[0]), a[1] = fmaf(vf, f.y, a[1]), a[2] = fmaf(vf, f.z, a[2]), a[3] = fmaf(vf, f.w, a[3]);
-              a[4] = fmaf(vr, q.x, a[4]), a[5] = fmaf(vr, q.y, a[5]), a[6] = fmaf(vr, q.z, a[6]), a[7] = fmaf(vr, q.w, a[7]);
+        const int bend = min(bb + BATCH, ee);
+#pragma unroll 2
+        for (int q0 = bb; q0 < bend; q0 += EPS) {   // sub-step: entries [q0, q0 + EPS), one per slot
+          const int src = min(q0 - bb + slot, 31);
+          const int e = q0 + slot;
+          const float vf0 = __shfl_sync(0xffffffffu, v_l, src), vr0 = __shfl_sync(0xffffffffu, rv_l, src);
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f), q = f;
+          const bool live = g_on && e < bend;
+          if (live) {
+            uint32_t code;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(st_base + src * 16 + g * 2));
+            const uint32_t addr = my_cb + code * 32 + ((code >> 2) & 1) * 16;  // cb_base is 32 B aligned
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                         : "r"(addr));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                         : "r"(addr ^ 16u));
+          }
+          const int qend = min(q0 + EPS, bend);
+          int j0 = q0;
+          while (j0 < qend) {   // pieces of this sub-step that belong to one row (almost always a single piece)
+            const int pend = min(re, qend);
+            const bool on = live && e >= j0 && e < pend;
+            const float vf = on ? vf0 : 0.f, vr = on ? vr0 : 0.f;
+            acc[0] = fmaf(vf, f.x, acc[0]), acc[1] = fmaf(vf, f.y, acc[1]), acc[2] = fmaf(vf, f.z, acc[2]), acc[3] = fmaf(vf, f.w, acc[3]);
+            acc[4] = fmaf(vr, q.x, acc[4]), acc[5] = fmaf(vr, q.y, acc[5]), acc[6] = fmaf(vr, q.z, acc[6]), acc[7] = fmaf(vr, q.w, acc[7]);
+            pending = true;
+            j0 = pend;
+            if (pend == re) {  // row r complete
+              flush(rs >= eb);
+              pending = false;
+              if (j0 >= ee) break;
+              next_row(j0);
             }
           }
-          pending = true;
-          j0 = pend;
-          if (pend == re) {  // row r complete: reduce over lanes and accumulate into the outputs
-            float o0, o1;
-            warp_reduce_scatter64(acc, lane, o0, o1);
-            emit(o0, o1, rs >= eb);
-#pragma unroll
-            for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-            pending = false;
-            if (j0 >= ee) break;
-            do {
-              ++r;
-              if (r - rbase >= 31) {
-                rbase = r;
-                rp_l = __ldg(rowptr + min(rbase + lane, B));
-              }
-              rs = __shfl_sync(0xffffffffu, rp_l, r - rbase);
-              re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
-            } while (re <= j0);
-          }
         }
       }
-      if (pending) {
-        float o0, o1;
-        warp_reduce_scatter64(acc, lane, o0, o1);
-        emit(o0, o1, false);
-      }
+      if (pending) flush(false);
     }
   }
 }
@@ -394,10 +384,10 @@ extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, con
   VQ_CHECK_ARG(G != 0, "mp_fwd_tail: needs D == 4, Wp == 8 and M <= 1024 (got M=%d D=%d Wp=%d)", M, D, Wp);
   VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31) && nb > 0, "mp_fwd_tail: bad sizes");
   VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_fwd_tail: needs chunk_row");
-  VQ_CHECK_ARG(ldy % 2 == 0 && ldx % 2 == 0 && (!gq || ldgq % 2 == 0) && aligned16(O) && aligned16(codes_g) &&
+  VQ_CHECK_ARG(ldy % 2 == 0 && ldx % 2 == 0 && (!gq || ldgq % 4 == 0) && aligned16(O) && aligned16(codes_g) &&
                    (reinterpret_cast<uintptr_t>(y) & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
-                   (!gq || (reinterpret_cast<uintptr_t>(gq) & 7) == 0),
-               "mp_fwd_tail: operands must be 8 B aligned with even leading dimensions");
+                   (!gq || aligned16(gq)),
+               "mp_fwd_tail: y / x must be 8 B aligned with even leading dimensions, gq 16 B aligned with ldgq % 4 == 0");
   VQ_CHECK_ARG(ws, "mp_fwd_tail: needs a workspace of vqgnn_mp_fwd_tail_workspace_bytes() bytes");
   VQ_CHECK_ARG(!info || gq, "mp_fwd_tail: info needs gq");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

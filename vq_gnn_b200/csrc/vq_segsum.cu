@@ -11,6 +11,7 @@
 // HBM-bound integer + gather work: B*nb*(8 B keys) sorted in ceil(log2(nb*M)/8) passes + one 16..32 B gather per
 // (row, branch).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
 
@@ -38,19 +39,69 @@ __global__ void segsum_bounds_kernel(const uint32_t* __restrict__ keys, int64_t 
   }
 }
 
+// Long codeword segments (early in training most rows share a few codewords) must not serialise one warp: every
+// segment is cut into fixed sub-ranges of kSegSub rows.  nsub[s] = ceil(len / kSegSub) (0 for an empty segment ->
+// one task that writes zeros is still needed, so max(1, .)); task_off = exclusive scan.  One warp per task.
+constexpr int kSegSub = 256;
+
+__global__ void segsum_nsub_kernel(const int32_t* __restrict__ seg_start, int S, int32_t* __restrict__ nsub) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int len = seg_start[s + 1] - seg_start[s];
+  nsub[s] = max(1, (len + kSegSub - 1) / kSegSub);
+}
+
+// z of one row (branch k) whitened exactly like the assignment kernels: fmaf(v, scale, shift)
+template <int NV>
+__device__ __forceinline__ void segsum_load(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g,
+                                            int64_t ldg, int64_t b, int k, int D, int Dg, int w_use, bool vec,
+                                            const float (&sc)[NV * 4], const float (&sh)[NV * 4],
+                                            float (&acc)[NV * 4]) {
+  if (vec) {   // D == Dg == 4 (or no g), 16 B aligned rows: two 128-bit loads
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * ldx + k * 4));
+    acc[0] += fmaf(xv.x, sc[0], sh[0]), acc[1] += fmaf(xv.y, sc[1], sh[1]);
+    acc[2] += fmaf(xv.z, sc[2], sh[2]), acc[3] += fmaf(xv.w, sc[3], sh[3]);
+    if constexpr (NV >= 2) {
+      if (g) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + b * ldg + k * 4));
+        acc[4] += fmaf(gv.x, sc[4], sh[4]), acc[5] += fmaf(gv.y, sc[5], sh[5]);
+        acc[6] += fmaf(gv.z, sc[6], sh[6]), acc[7] += fmaf(gv.w, sc[7], sh[7]);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int w = 0; w < NV * 4; ++w) {
+    float v = 0.f;
+    if (w < D) v = fmaf(__ldg(x + b * ldx + k * D + w), sc[w], sh[w]);
+    else if (w < w_use) v = fmaf(__ldg(g + b * ldg + k * Dg + (w - D)), sc[w], sh[w]);
+    acc[w] += v;
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256)
     segsum_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g, int64_t ldg,
                   const float* __restrict__ scale, const float* __restrict__ shift,
-                  const uint32_t* __restrict__ rows, const int32_t* __restrict__ seg_start, int S, int nbc, int M,
-                  int D, int Dg, int Wp, float* __restrict__ stats) {
+                  const uint32_t* __restrict__ rows, const int32_t* __restrict__ seg_start,
+                  const int32_t* __restrict__ task_off, int S, int max_tasks, int nbc, int M, int D, int Dg, int Wp,
+                  int vec, float* __restrict__ stats, float* __restrict__ part) {
   const int lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (seg >= S) return;
+  const int task = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (task >= max_tasks || task >= __ldg(task_off + S)) return;
+  int lo = 0, hi = S;   // largest seg with task_off[seg] <= task
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(task_off + mid) <= task) lo = mid;
+    else hi = mid;
+  }
+  const int seg = lo, sub = task - __ldg(task_off + seg);
+  const int nsub = __ldg(task_off + seg + 1) - __ldg(task_off + seg);
   const int k = seg / M;
   const int C = nbc * D;
   const int w_use = D + (g ? Dg : 0);
-  const int s0 = __ldg(seg_start + seg), s1 = __ldg(seg_start + seg + 1);
+  const int s0 = __ldg(seg_start + seg) + sub * kSegSub;
+  const int s1 = min(__ldg(seg_start + seg + 1), s0 + kSegSub);
   float sc[NV * 4], sh[NV * 4];
 #pragma unroll
   for (int w = 0; w < NV * 4; ++w) {
@@ -61,25 +112,43 @@ __global__ void __launch_bounds__(256)
   float acc[NV * 4];
 #pragma unroll
   for (int w = 0; w < NV * 4; ++w) acc[w] = 0.f;
-  for (int i = s0 + lane; i < s1; i += 32) {
-    const int64_t b = __ldg(rows + i);
-#pragma unroll
-    for (int w = 0; w < NV * 4; ++w) {
-      float v = 0.f;
-      if (w < D) v = fmaf(__ldg(x + b * ldx + k * D + w), sc[w], sh[w]);
-      else if (w < w_use) v = fmaf(__ldg(g + b * ldg + k * Dg + (w - D)), sc[w], sh[w]);
-      acc[w] += v;
-    }
-  }
+  for (int i = s0 + lane; i < s1; i += 32)
+    segsum_load<NV>(x, ldx, g, ldg, static_cast<int64_t>(__ldg(rows + i)), k, D, Dg, w_use, vec != 0, sc, sh, acc);
 #pragma unroll
   for (int w = 0; w < NV * 4; ++w) acc[w] = warp_sum(acc[w]);   // fixed xor tree: order independent of timing
-  float* dst = stats + static_cast<int64_t>(seg) * (Wp + 4);
-  if (lane == 0) {
+  if (lane != 0) return;
+  if (nsub == 1) {
+    float* dst = stats + static_cast<int64_t>(seg) * (Wp + 4);
 #pragma unroll
     for (int w = 0; w < NV * 4; ++w)
       if (w < Wp) dst[w] = w < w_use ? acc[w] : 0.f;
     for (int w = NV * 4; w < Wp; ++w) dst[w] = 0.f;
-    dst[Wp] = static_cast<float>(s1 - s0);
+    dst[Wp] = static_cast<float>(__ldg(seg_start + seg + 1) - __ldg(seg_start + seg));
+    dst[Wp + 1] = 0.f, dst[Wp + 2] = 0.f, dst[Wp + 3] = 0.f;
+  } else {
+    float* dst = part + static_cast<int64_t>(task) * (NV * 4);
+#pragma unroll
+    for (int w = 0; w < NV * 4; ++w) dst[w] = acc[w];
+  }
+}
+
+// segments cut into several sub-ranges: their partial sums added in sub-range order (thread per (segment, column))
+template <int NV>
+__global__ void segsum_combine_kernel(const int32_t* __restrict__ seg_start, const int32_t* __restrict__ task_off,
+                                      int S, int w_use, int Wp, const float* __restrict__ part,
+                                      float* __restrict__ stats) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int seg = static_cast<int>(i / (NV * 4)), w = static_cast<int>(i - static_cast<int64_t>(seg) * (NV * 4));
+  if (seg >= S) return;
+  const int t0 = __ldg(task_off + seg), nsub = __ldg(task_off + seg + 1) - t0;
+  if (nsub <= 1) return;
+  float t = 0.f;
+  for (int j = 0; j < nsub; ++j) t += part[static_cast<int64_t>(t0 + j) * (NV * 4) + w];
+  float* dst = stats + static_cast<int64_t>(seg) * (Wp + 4);
+  if (w < Wp) dst[w] = w < w_use ? t : 0.f;
+  if (w == 0) {
+    for (int u = NV * 4; u < Wp; ++u) dst[u] = 0.f;
+    dst[Wp] = static_cast<float>(__ldg(seg_start + seg + 1) - __ldg(seg_start + seg));
     dst[Wp + 1] = 0.f, dst[Wp + 2] = 0.f, dst[Wp + 3] = 0.f;
   }
 }
@@ -103,10 +172,19 @@ static size_t cub_sort_bytes(int64_t n, int bits) {
 
 using namespace vqgnn;
 
+static size_t cub_scan_bytes(int64_t n) {
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr),
+                                static_cast<int>(n));
+  return tmp;
+}
+static int64_t segsum_max_tasks(int64_t n, int64_t S) { return n / kSegSub + S + 1; }
+
 extern "C" size_t vqgnn_vq_segsum_workspace_bytes(int64_t B, int nbc, int M) {
   const int64_t n = B * nbc, S = static_cast<int64_t>(nbc) * M;
-  return 4 * align256(static_cast<size_t>(n) * 4) + align256(static_cast<size_t>(S + 1) * 4) +
-         align256(cub_sort_bytes(n, key_bits(S))) + 256;
+  return 4 * align256(static_cast<size_t>(n) * 4) + 3 * align256(static_cast<size_t>(S + 2) * 4) +
+         align256(std::max(cub_sort_bytes(n, key_bits(S)), cub_scan_bytes(S + 1))) +
+         align256(static_cast<size_t>(segsum_max_tasks(n, S)) * 20 * 4) + 256;
 }
 
 extern "C" int vqgnn_vq_segsum(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
@@ -126,10 +204,16 @@ extern "C" int vqgnn_vq_segsum(const float* x, int64_t ldx, const float* g, int6
   uint32_t* keys_out = reinterpret_cast<uint32_t*>(p + an);
   uint32_t* rows_in = reinterpret_cast<uint32_t*>(p + 2 * an);
   uint32_t* rows_out = reinterpret_cast<uint32_t*>(p + 3 * an);
+  const size_t as = align256(static_cast<size_t>(S + 2) * 4);
   int32_t* seg_start = reinterpret_cast<int32_t*>(p + 4 * an);
-  void* cub_tmp = p + 4 * an + align256(static_cast<size_t>(S + 1) * 4);
+  int32_t* nsub = reinterpret_cast<int32_t*>(p + 4 * an + as);
+  int32_t* task_off = reinterpret_cast<int32_t*>(p + 4 * an + 2 * as);
+  void* cub_tmp = p + 4 * an + 3 * as;
   const int bits = key_bits(S);
   size_t cub_bytes = cub_sort_bytes(n, bits);
+  const size_t cub_cap = align256(std::max(cub_bytes, cub_scan_bytes(S + 1)));
+  float* part = reinterpret_cast<float*>(static_cast<char*>(cub_tmp) + cub_cap);
+  const int max_tasks = static_cast<int>(segsum_max_tasks(n, S));
   const int grid = static_cast<int>(std::min<int64_t>((n + 255) / 256, 16 * kNumSMs));
   segsum_keys_kernel<<<grid, 256, 0, s>>>(idx, n, nbc, M, keys_in, rows_in);
   VQ_LAUNCH_CHECK();
@@ -137,12 +221,27 @@ extern "C" int vqgnn_vq_segsum(const float* x, int64_t ldx, const float* g, int6
   count_launch(2);
   segsum_bounds_kernel<<<grid, 256, 0, s>>>(keys_out, n, static_cast<int>(S), seg_start);
   VQ_LAUNCH_CHECK();
+  // sub-range tasks: nsub per segment, exclusive scan over S + 1 entries (the last one = total)
+  segsum_nsub_kernel<<<ceil_div(S, 256), 256, 0, s>>>(seg_start, (int)S, nsub);
+  VQ_LAUNCH_CHECK();
+  VQ_CUDA(cudaMemsetAsync(nsub + S, 0, sizeof(int32_t), s));
+  size_t scan_b = cub_scan_bytes(S + 1);
+  VQ_CUDA(cub::DeviceScan::ExclusiveSum(cub_tmp, scan_b, nsub, task_off, static_cast<int>(S + 1), s));
+  count_launch(1);
   const int w_use = D + (g ? Dg : 0);
   const int nv = (w_use + 3) / 4;
-  const int sgrid = static_cast<int>((S + 7) / 8);
+  const int vec = (D == 4 && (!g || Dg == 4) && ldx % 4 == 0 && (!g || ldg % 4 == 0) &&
+                   (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!g || (reinterpret_cast<uintptr_t>(g) & 15) == 0))
+                      ? 1 : 0;
+  const int sgrid = (max_tasks + 7) / 8;
 #define VQ_SEGSUM(NV)                                                                                          \
-  segsum_kernel<NV><<<sgrid, 256, 0, s>>>(x, ldx, g, ldg, scale, shift, rows_out, seg_start, (int)S, nbc, M, D, \
-                                          g ? Dg : 0, Wp, stats)
+  do {                                                                                                         \
+    segsum_kernel<NV><<<sgrid, 256, 0, s>>>(x, ldx, g, ldg, scale, shift, rows_out, seg_start, task_off, (int)S, \
+                                            max_tasks, nbc, M, D, g ? Dg : 0, Wp, vec, stats, part);           \
+    segsum_combine_kernel<NV><<<ceil_div(S * (NV * 4), 256), 256, 0, s>>>(seg_start, task_off, (int)S, w_use,  \
+                                                                         Wp, part, stats);                     \
+    count_launch(1);                                                                                           \
+  } while (0)
   switch (nv) {
     case 1: VQ_SEGSUM(1); break;
     case 2: VQ_SEGSUM(2); break;
