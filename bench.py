@@ -238,6 +238,7 @@ def train_step(cfg, model, head, opt, x, plan, y, distributed: bool):
         params = list(model.parameters()) + (list(head.parameters()) if head is not None else [])
         vdist.allreduce_mean_grads_(params)
     opt.step()
+    model.join_vq_updates()      # side-stream VQ updates (if enabled) re-join here: the step is self-contained
     return loss
 
 
@@ -412,6 +413,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true",
                     help="launch the device-resident steps eagerly instead of replaying one CUDA graph per batch")
+    ap.add_argument("--sync-vq", action="store_true",
+                    help="run the VQ hook updates on the compute stream (default: side stream, off the critical path)")
     ap.add_argument("--cpu-batch", type=int, default=0, help="batch nodes of the CPU arm's sample (0 = the config's B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -488,6 +491,7 @@ def main():
         torch.distributed.all_reduce(cap, op=torch.distributed.ReduceOp.MAX)
         capacity = int(cap.item())
     model, head = build_model(c, dev, N, distributed, args.assign_impl, capacity)
+    model.set_async_vq_updates(not args.sync_vq)
     use_graphs = not args.no_graphs
     params = list(model.parameters()) + (list(head.parameters()) if head is not None else [])
     opt = torch.optim.RMSprop(params, lr=c["lr"], alpha=0.99, capturable=use_graphs)
@@ -736,7 +740,8 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "replica_max_abs_diff": replica_div, "graph_identical_on_all_ranks": graph_identical,
                 "batch_nodes_per_rank": [int(b[0].shape[0]) for b in batches],
-                "cuda_graphs": graphs is not None, "kernels": kernel_table, "assign_impl": impl_name}
+                "cuda_graphs": graphs is not None, "kernels": kernel_table, "assign_impl": impl_name,
+                "vq_updates": "compute stream" if args.sync_vq else "side stream (overlapped with the rest of backward)"}
         print(json.dumps(line), flush=True)
     if distributed:
         torch.distributed.barrier()

@@ -345,3 +345,42 @@ def test_v2_device_plan_matches_torch_builder(conv):
         return t.index_put_((plan.bwd_col.long(), bj), plan.bwd_val.double(), accumulate=True)
     assert torch.equal(dense_bwd(p_t), dense_bwd(p_d))
     assert torch.equal(p_t.bwd_rowptr, p_d.bwd_rowptr) and p_t.bwd_col.numel() == p_d.bwd_col.numel()
+
+
+@pytest.mark.parametrize("version,conv", [("v2", "GCN"), ("v1", "SAGE")])
+def test_side_stream_vq_updates_are_bit_identical(version, conv):
+    """VQBank.async_update: the hook's update runs on a side stream and re-joins before the layer's next forward;
+    training must be bit-identical to the in-line update (the path has no order-dependent float accumulation)."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    N, B, M, C = 700, 160, 16, 12
+    g = H.make_graph(N, 6000, conv, version, seed=9)
+    bAs = [H.batch_to(H.make_batch(g, B, version, seed=s), dev) for s in range(3)]
+    xs = [torch.randn(B, C, generator=torch.Generator().manual_seed(s)).to(dev) for s in range(3)]
+    ys = [torch.randint(0, 7, (B,), generator=torch.Generator().manual_seed(20 + s)).to(dev) for s in range(3)]
+
+    def run(async_flag):
+        torch.manual_seed(0)
+        m = V.LowRankGNN(C, 16, 7, 3, 0., M, 4, N, no_second_fc=True, skip=False, commitment_cost=0.,
+                         grad_scale=[1, 1], act='leaky_gelu', bn_flag=True, warm_up_flag=True, conv_type=conv,
+                         version=version).to(dev).train()
+        m.set_async_vq_updates(async_flag)
+        opt = torch.optim.RMSprop(m.parameters(), lr=1e-3)
+        losses = []
+        for i in range(6):
+            if i == 1:
+                m.set_inited(True)
+            opt.zero_grad()
+            out, _, info = m((xs[i % 3], bAs[i % 3]), 1)
+            loss = F.cross_entropy(out, ys[i % 3]) + info
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        m.join_vq_updates()
+        torch.cuda.synchronize()
+        return losses, {k: v.clone() for k, v in m.state_dict().items()}
+    l0, s0 = run(False)
+    l1, s1 = run(True)
+    assert l0 == l1
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k

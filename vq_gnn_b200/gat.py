@@ -93,7 +93,7 @@ class VQGATFunction(torch.autograd.Function):
             _lib.ptr(dx), dx.stride(0) if dx is not None else 0, _lib.ptr(datt_l), _lib.ptr(datt_r), st))
         if ctx.fire_hook:
             # the hook sees d loss / d (un-normalised conv output)[:B, :C]  (vq_gnn_v2/models.py:181-185)
-            bank.run(x, dyn, plan.batch_idx, True)
+            bank.update(x, dyn, plan.batch_idx)
         return dx, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), None, None, None, None, None
 
 
@@ -154,7 +154,7 @@ class VQGAT1Function(torch.autograd.Function):
             dx.stride(0) if dx is not None else 0, _lib.ptr(datt_l), _lib.ptr(datt_r), st))
         if ctx.fire_hook:
             # hook(grad) on X_output_B [B, D+1] of every branch (vq_gnn_v1/models.py:199-203): add_flag width
-            bank.run(x, gy, plan.batch_idx, True)
+            bank.update(x, gy, plan.batch_idx)
         return dx, datt_l, datt_r, None, None, None, None, None
 
 

@@ -147,7 +147,7 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
         if ctx.fire_hook:
             # the reference's hook(grad): vq.update(X_B, grad) ; c_indices[batch] = idx ; return grad
-            bank.run(x, dy, plan.batch_idx, True)
+            bank.update(x, dy, plan.batch_idx)
         return dx, None, None, None, None, None
 
 
@@ -365,6 +365,7 @@ class LowRankGNNLayer(nn.Module):
         x = x.float()
         xc = x if x.is_contiguous() else x.contiguous()
         inited = self.inited
+        self.bank.join()             # a pending side-stream update of this layer's quantisers (bank.async_update)
         self.bank.poll_status()      # deferred 'Bad Init!' check of an earlier update: no stream stall
         do_init = (not inited or unlabeled) and (self.training or self.version == 'v2')
         if do_init:          # models.py:165-166 (v2) / v1 models.py:164-165: feature-only warm start
@@ -493,6 +494,17 @@ class LowRankGNN(nn.Module):
     def check_status(self):
         for layer in self.convs:
             layer.check_status()
+
+    def set_async_vq_updates(self, flag: bool = True):
+        """Run the hook's VQ updates on a side stream (VQBank.async_update): they only prepare the NEXT step."""
+        for layer in self.convs:
+            layer.bank.async_update = bool(flag)
+
+    def join_vq_updates(self):
+        """Order the current stream after every pending side-stream VQ update.  Each layer's next forward does this by
+        itself; call it explicitly before reading quantiser state or before a CUDA-graph capture of the step ends."""
+        for layer in self.convs:
+            layer.bank.join()
 
     def inference(self, x, A):
         raise NotImplementedError("LowRankGNN.inference is broken in the reference v2 (models.py:355) "

@@ -56,6 +56,12 @@ class VQBank:
         # bring the same batch size, which is then verified with one small allreduce per update
         self.gather_capacity: Optional[int] = None
         self._status_host = None           # (pinned int32, event) of the last asynchronous status read
+        # True: the hook's update (which only prepares state for the NEXT step, vq_gnn_v2/models.py:39-56 returns
+        # `grad` unchanged) runs on a side stream, overlapping the rest of the backward pass and -- multi-GPU -- taking
+        # its three collectives off the critical path; `join()` (called by the layer's next forward, or explicitly
+        # through LowRankGNN.join_vq_updates() before a CUDA-graph capture ends) orders later readers after it
+        self.async_update = False
+        self._pending = False
         # 0: exact-fp32 SIMT kernel (default: bit-stable codes, the parity anchor), 1: tcgen05 3xTF32 kernel,
         # 'auto': tcgen05 when it is the faster one (M >= 512 and a packed width it supports; measured on B200:
         # 0.55 vs 0.45 ms at M = 256, 0.57 vs 0.89 at M = 1024, 0.62 vs 1.41 at M = 4096)
@@ -230,8 +236,42 @@ class VQBank:
         self.last_stats = stats
         return idx
 
+    # ---- the hook's update, optionally off the critical path ----------------------------------------
+    _SIDE = {}
+
+    @classmethod
+    def side_stream(cls, dev) -> "torch.cuda.Stream":
+        """ONE side stream per device, shared by every bank: the updates (and their collectives) of all layers stay in
+        program order, which is the same on every rank."""
+        key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+        st = cls._SIDE.get(key)
+        if st is None:
+            st = cls._SIDE[key] = torch.cuda.Stream(device=dev)
+        return st
+
+    def update(self, x: Tensor, g: Tensor, batch_idx: Tensor) -> None:
+        """The VQ hook body: vq.update(X_B, grad); c_indices[batch] = idx  (vq_gnn_v2/models.py:39-46)."""
+        if not self.async_update:
+            self.run(x, g, batch_idx, True)
+            return
+        cur = torch.cuda.current_stream(x.device)
+        side = self.side_stream(x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.run(x, g, batch_idx, True)
+        for t in (x, g, batch_idx):
+            t.record_stream(side)
+        self._pending = True
+
+    def join(self) -> None:
+        """Order the current stream after a pending asynchronous update of this bank."""
+        if self._pending:
+            torch.cuda.current_stream(self.E.device).wait_stream(self.side_stream(self.E.device))
+            self._pending = False
+
     def check_status(self):
         """'Bad Init!' check (vq.py:188-189, 253-254): one host sync."""
+        self.join()
         if self.status.is_cuda and int(self.status.item()) & 1:
             self.status.zero_()
             self._status_host = None
