@@ -175,8 +175,38 @@ __global__ void __launch_bounds__(kTailThreads, 1)
           if (lane < BATCH && e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
         }
         const int bend = min(bb + BATCH, ee);
-#pragma unroll 2
-        for (int q0 = bb; q0 < bend; q0 += EPS) {   // sub-step: entries [q0, q0 + EPS), one per slot
+        const uint32_t my_st = st_base + slot * 16 + g * 2;
+        if (bend - bb == BATCH && bend <= re) {
+          // fast path (the usual case: rows are hundreds of entries long): the whole batch belongs to the current row,
+          // no row bookkeeping inside -- per sub-step 2 SHFL + 1 LDS.U16 + 2 LDS.128 + 8 FFMA per lane
+#pragma unroll
+          for (int j = 0; j < BATCH / EPS; ++j) {
+            const float vf = __shfl_sync(0xffffffffu, v_l, j * EPS + slot);
+            const float vr = __shfl_sync(0xffffffffu, rv_l, j * EPS + slot);
+            if (g_on) {
+              uint32_t code;
+              asm("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(my_st + j * EPS * 16));
+              const uint32_t addr = my_cb + code * 32 + ((code >> 2) & 1) * 16;  // cb_base is 32 B aligned
+              float4 f, q;
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                           : "r"(addr));
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                           : "r"(addr ^ 16u));
+              acc[0] = fmaf(vf, f.x, acc[0]), acc[1] = fmaf(vf, f.y, acc[1]), acc[2] = fmaf(vf, f.z, acc[2]), acc[3] = fmaf(vf, f.w, acc[3]);
+              acc[4] = fmaf(vr, q.x, acc[4]), acc[5] = fmaf(vr, q.y, acc[5]), acc[6] = fmaf(vr, q.z, acc[6]), acc[7] = fmaf(vr, q.w, acc[7]);
+            }
+          }
+          pending = true;
+          if (bend == re) {
+            flush(rs >= eb);
+            pending = false;
+            if (bend < ee) next_row(bend);
+          }
+          continue;
+        }
+        for (int q0 = bb; q0 < bend; q0 += EPS) {   // general path: the batch holds a row boundary (or is ragged)
           const int src = min(q0 - bb + slot, 31);
           const int e = q0 + slot;
           const float vf0 = __shfl_sync(0xffffffffu, v_l, src), vr0 = __shfl_sync(0xffffffffu, rv_l, src);
@@ -185,7 +215,7 @@ __global__ void __launch_bounds__(kTailThreads, 1)
           if (live) {
             uint32_t code;
             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(st_base + src * 16 + g * 2));
-            const uint32_t addr = my_cb + code * 32 + ((code >> 2) & 1) * 16;  // cb_base is 32 B aligned
+            const uint32_t addr = my_cb + code * 32 + ((code >> 2) & 1) * 16;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
                          : "r"(addr));
@@ -195,7 +225,7 @@ __global__ void __launch_bounds__(kTailThreads, 1)
           }
           const int qend = min(q0 + EPS, bend);
           int j0 = q0;
-          while (j0 < qend) {   // pieces of this sub-step that belong to one row (almost always a single piece)
+          while (j0 < qend) {   // pieces of this sub-step that belong to one row
             const int pend = min(re, qend);
             const bool on = live && e >= j0 && e < pend;
             const float vf = on ? vf0 : 0.f, vr = on ? vr0 : 0.f;
