@@ -5,7 +5,8 @@
 // by the L1tex wavefront rate (profiles/r1_mp_fwd_ncu_full.txt: 484 M sectors, 1.2 sectors/clk/SM).  For the v1
 // formulation (vq_gnn_v1/utils/dataloader.py:144-192 `mapper` + vq_gnn_v1/models.py:170-223), where every batch
 // row has hundreds of out-of-batch neighbours, this kernel instead
-//   * keeps the de-whitened codebooks O_k of G consecutive branches in shared memory (G*M*32 B <= 192 KB),
+//   * keeps one HALF (feature or gradient columns) of the de-whitened codebooks O_k of G = 8 consecutive branches
+//     in shared memory (M*128 B <= 192 KB), laid out so that the gathers are bank-conflict free,
 //   * reads the G codes of a neighbour with ONE 16 B load from a group-major copy of the code table
 //     (codes_g [ceil(nb/G)][N][8] int16), i.e. one global sector per (entry, group) instead of G,
 //   * gathers codewords with LDS.128 (16 B chunk index XOR-swizzled so random codes spread over all banks),
@@ -31,11 +32,16 @@ __device__ __forceinline__ void red_v4(float* p, const float (&v)[4]) {
                : "memory");
 }
 
-// Lane mapping: a warp works on EPS = 32 / G entries at a time; lane = slot * G + g handles branch g of the group
-// for the entry in `slot` and keeps only that branch's 8 partial sums (4 feature + 4 gradient columns) in
-// registers -- 8 accumulators per lane instead of 64 (lane = entry), which lets 32 warps share the SM and removes the
-// 62-shuffle reduce-scatter: a row ends with EPS shuffles per column into the slot-0 lanes.
-template <int G>
+// Lane mapping: G = 8 branches per group; a warp advances 4 entries per sub-step, lane = slot * 8 + g gathers branch
+// g's codeword HALF (4 floats, one LDS.128) of the entry in `slot`.  The two halves are separate passes ("half
+// groups"): features -> y with val * feat_scale, gradients -> gq with rval.
+// Shared-memory layout of a half group: chunk (code, g) at byte code * 128 + g * 16, i.e. the eight lanes of an
+// LDS.128 phase (one entry's eight branches) always hit eight DIFFERENT 16 B bank groups whatever the codes are:
+// the random gathers are bank-conflict free by construction (M * 128 B <= 192 KB: M <= 1536).
+constexpr int kTailG = 8;
+constexpr int kTailEPS = 4;     // entries per sub-step
+constexpr int kTailBatch = 32;  // entries staged per batch (one per lane)
+
 __global__ void __launch_bounds__(kTailThreads, 1)
     mp_tail_smem_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ node,
                         const float* __restrict__ val, const float* __restrict__ rval,
@@ -44,49 +50,54 @@ __global__ void __launch_bounds__(kTailThreads, 1)
                         float feat_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ gq, int64_t ldgq,
                         float* __restrict__ py, float* __restrict__ pgq, int C, int ng, int cpi,
                         int items_per_group) {
-  constexpr int EPS = 32 / G;          // entries per sub-step (4 for G = 8, 5 for G = 6)
-  constexpr int BATCH = 32 / EPS * EPS;  // entries staged per batch (32 / 30): one per lane
-  extern __shared__ __align__(128) unsigned char cb_smem[];  // [G][M] codewords of 32 B, 16 B chunks swizzled
+  constexpr int G = kTailG, EPS = kTailEPS, BATCH = kTailBatch;
+  extern __shared__ __align__(128) unsigned char cb_smem[];  // [M][8] chunks of 16 B
   __shared__ uint4 stage[kTailWarps][32];                    // per warp: the batch's code vectors (8 int16 each)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* cb_ptr = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cb_smem) + 127) & ~uintptr_t(127));
   const uint32_t cb_base = static_cast<uint32_t>(__cvta_generic_to_shared(cb_ptr));
   const uint32_t st_base = static_cast<uint32_t>(__cvta_generic_to_shared(&stage[warp][0]));
-  const int branch_bytes = M * 32;
-  const int slot = lane / G, g = lane - slot * G;
-  const bool lane_on = slot < EPS;
+  const int slot = lane >> 3, g = lane & 7;
   __shared__ int next_chunk;  // warps of the CTA draw the item's chunks dynamically
   if (d_nnz) {  // entry count only known on the device (vqgnn_plan_v1_build): the host sized the grid by an upper bound
     nnz = __ldg(d_nnz);
     n_chunks = (nnz + chunk - 1) / chunk;
   }
   int loaded = -1;
-  const int n_items = ng * items_per_group;
+  const int nhg = 2 * ng;   // half groups: (group, half)
+  const int n_items = nhg * items_per_group;
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int gk = item / items_per_group;
-    const int cblk = item - gk * items_per_group;
+    const int hg = item / items_per_group;
+    const int cblk = item - hg * items_per_group;
+    const int gk = hg >> 1, half = hg & 1;
+    if (half == 1 && gq == nullptr) continue;   // uniform over the CTA
     const int kbase = gk * G;
     const int gcount = min(G, nb - kbase);
-    if (gk != loaded) {  // (re)load the group's codebooks: coalesced 16 B loads, swizzled 16 B stores
+    if (hg != loaded) {  // (re)load the half group's codewords into the conflict-free layout
       __syncthreads();
-      const int chunks16 = gcount * M * 2;
-      const float4* src = reinterpret_cast<const float4*>(O + static_cast<int64_t>(kbase) * M * 8);
-      for (int c = threadIdx.x; c < chunks16; c += kTailThreads) {
-        const int m = (c >> 1) % M;  // codeword index inside its branch
-        const int sw = (m >> 2) & 1;
-        *reinterpret_cast<float4*>(cb_ptr + static_cast<size_t>(c ^ sw) * 16) = __ldg(src + c);
+      const int n16 = gcount * M;
+      for (int c = threadIdx.x; c < n16; c += kTailThreads) {
+        const int gI = c / M, m = c - gI * M;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(O + (static_cast<int64_t>(kbase + gI) * M + m) * 8 + half * 4));
+        *reinterpret_cast<float4*>(cb_ptr + (static_cast<size_t>(m) * 8 + gI) * 16) = v;
       }
-      loaded = gk;
+      loaded = hg;
       __syncthreads();
     }
     const int16_t* cg = codes_g + static_cast<int64_t>(gk) * N * 8;
+    const float* wsrc = half ? rval : val;
+    const float wscale = half ? 1.f : feat_scale;
+    float* out = half ? gq : y;
+    const int64_t ldo = half ? ldgq : ldy;
+    float* pout = half ? pgq : py;
     const int c_begin = cblk * cpi, c_end = min(c_begin + cpi, n_chunks);
     __syncthreads();  // every warp is done with the previous item (and its chunk counter)
     if (threadIdx.x == 0) next_chunk = c_begin;
     __syncthreads();
-    const bool g_on = lane_on && g < gcount;
-    const uint32_t my_cb = cb_base + g * branch_bytes;
+    const bool g_on = g < gcount;
+    const uint32_t my_cb = cb_base + g * 16;
+    const uint32_t my_st = st_base + slot * 16 + g * 2;
     const int colbase = (kbase + g) * 4;
 
     while (true) {
@@ -95,39 +106,31 @@ __global__ void __launch_bounds__(kTailThreads, 1)
       ch = __shfl_sync(0xffffffffu, ch, 0);
       if (ch >= c_end) break;
       const int eb = ch * chunk, ee = min(eb + chunk, nnz);
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
       // rows: lane i holds rowptr[rbase + i]
       int r = __ldg(chunk_row + ch);
       int rbase = r;
       int rp_l = __ldg(rowptr + min(rbase + lane, B));
       int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
 
-      // the row segment [.., seg_end) is complete: sum the EPS slots of every column into the slot-0 lanes and emit
+      // the current row segment is complete: sum the 4 slots of every column into the slot-0 lanes and emit
       auto flush = [&](bool whole) {
-        float t[8];
+        float t[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           t[i] = acc[i];
 #pragma unroll
-          for (int sI = 1; sI < EPS; ++sI) t[i] += __shfl_sync(0xffffffffu, acc[i], min(sI * G + g, 31));
+          for (int sI = 1; sI < EPS; ++sI) t[i] += __shfl_sync(0xffffffffu, acc[i], sI * G + g);
           acc[i] = 0.f;
         }
-        if (slot == 0 && g < gcount) {
+        if (slot == 0 && g_on) {
           const int kind = piece_kind(whole, rs, re, eb, chunk);
-          const int64_t poff = (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + colbase;
-          const float tf[4] = {t[0], t[1], t[2], t[3]}, tq[4] = {t[4], t[5], t[6], t[7]};
-          float* yp = y + static_cast<int64_t>(r) * ldy + colbase;
-          if (kind == kPieceWhole) *reinterpret_cast<float4*>(yp) = make_float4(tf[0], tf[1], tf[2], tf[3]);
-          else if (kind == kPieceRed) red_v4(yp, tf);
-          else *reinterpret_cast<float4*>(py + poff) = make_float4(tf[0], tf[1], tf[2], tf[3]);
-          if (gq) {
-            float* gp = gq + static_cast<int64_t>(r) * ldgq + colbase;
-            if (kind == kPieceWhole) *reinterpret_cast<float4*>(gp) = make_float4(tq[0], tq[1], tq[2], tq[3]);
-            else if (kind == kPieceRed) red_v4(gp, tq);
-            else *reinterpret_cast<float4*>(pgq + poff) = make_float4(tq[0], tq[1], tq[2], tq[3]);
-          }
+          float* dst = out + static_cast<int64_t>(r) * ldo + colbase;
+          if (kind == kPieceWhole) *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+          else if (kind == kPieceRed) red_v4(dst, t);
+          else
+            *reinterpret_cast<float4*>(pout + (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C +
+                                       colbase) = make_float4(t[0], t[1], t[2], t[3]);
         }
       };
       auto next_row = [&](int upto) {   // advance to the row that holds entry `upto`
@@ -142,60 +145,55 @@ __global__ void __launch_bounds__(kTailThreads, 1)
         } while (re <= upto);
       };
 
-      // software pipeline: (node, val, rval) two batches ahead, code vectors one batch ahead
+      // software pipeline: (node, weight) two batches ahead, code vectors one batch ahead
       int node_n = 0;
-      float v_n = 0.f, rv_n = 0.f;
+      float v_n = 0.f;
       uint4 cv_n = make_uint4(0, 0, 0, 0);
       {
         const int e = eb + lane;
-        if (lane < BATCH && e < ee) node_n = __ldg(node + e), v_n = __ldg(val + e), rv_n = __ldg(rval + e);
+        if (e < ee) node_n = __ldg(node + e), v_n = __ldg(wsrc + e);
         cv_n = __ldg(reinterpret_cast<const uint4*>(cg + static_cast<int64_t>(node_n) * 8));
       }
       int node_nn = 0;
-      float v_nn = 0.f, rv_nn = 0.f;
+      float v_nn = 0.f;
       {
         const int e = eb + BATCH + lane;
-        if (lane < BATCH && e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
+        if (e < ee) node_nn = __ldg(node + e), v_nn = __ldg(wsrc + e);
       }
       bool pending = false;
 
       for (int bb = eb; bb < ee; bb += BATCH) {
-        const float v_l = v_n * feat_scale, rv_l = rv_n;
+        const float v_l = v_n * wscale;
         __syncwarp();
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(st_base + lane * 16), "r"(cv_n.x), "r"(cv_n.y),
                      "r"(cv_n.z), "r"(cv_n.w)
                      : "memory");
         __syncwarp();
         // advance the pipeline
-        node_n = node_nn, v_n = v_nn, rv_n = rv_nn;
+        node_n = node_nn, v_n = v_nn;
         cv_n = __ldg(reinterpret_cast<const uint4*>(cg + static_cast<int64_t>(node_n) * 8));
         {
           const int e = bb + 2 * BATCH + lane;
-          node_nn = 0, v_nn = 0.f, rv_nn = 0.f;
-          if (lane < BATCH && e < ee) node_nn = __ldg(node + e), v_nn = __ldg(val + e), rv_nn = __ldg(rval + e);
+          node_nn = 0, v_nn = 0.f;
+          if (e < ee) node_nn = __ldg(node + e), v_nn = __ldg(wsrc + e);
         }
         const int bend = min(bb + BATCH, ee);
-        const uint32_t my_st = st_base + slot * 16 + g * 2;
         if (bend - bb == BATCH && bend <= re) {
           // fast path (the usual case: rows are hundreds of entries long): the whole batch belongs to the current row,
-          // no row bookkeeping inside -- per sub-step 2 SHFL + 1 LDS.U16 + 2 LDS.128 + 8 FFMA per lane
+          // no row bookkeeping inside -- per sub-step 1 SHFL + 1 LDS.U16 + 1 conflict-free LDS.128 + 4 FFMA per lane
+          uint32_t code[BATCH / EPS];
+#pragma unroll
+          for (int j = 0; j < BATCH / EPS; ++j)
+            asm("ld.shared.u16 %0, [%1];" : "=r"(code[j]) : "r"(my_st + j * EPS * 16));
 #pragma unroll
           for (int j = 0; j < BATCH / EPS; ++j) {
             const float vf = __shfl_sync(0xffffffffu, v_l, j * EPS + slot);
-            const float vr = __shfl_sync(0xffffffffu, rv_l, j * EPS + slot);
             if (g_on) {
-              uint32_t code;
-              asm("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(my_st + j * EPS * 16));
-              const uint32_t addr = my_cb + code * 32 + ((code >> 2) & 1) * 16;  // cb_base is 32 B aligned
-              float4 f, q;
+              float4 f;
               asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                           : "r"(addr));
-              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
-                           : "r"(addr ^ 16u));
+                  : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                  : "r"(my_cb + code[j] * 128));
               acc[0] = fmaf(vf, f.x, acc[0]), acc[1] = fmaf(vf, f.y, acc[1]), acc[2] = fmaf(vf, f.z, acc[2]), acc[3] = fmaf(vf, f.w, acc[3]);
-              acc[4] = fmaf(vr, q.x, acc[4]), acc[5] = fmaf(vr, q.y, acc[5]), acc[6] = fmaf(vr, q.z, acc[6]), acc[7] = fmaf(vr, q.w, acc[7]);
             }
           }
           pending = true;
@@ -207,30 +205,25 @@ __global__ void __launch_bounds__(kTailThreads, 1)
           continue;
         }
         for (int q0 = bb; q0 < bend; q0 += EPS) {   // general path: the batch holds a row boundary (or is ragged)
-          const int src = min(q0 - bb + slot, 31);
+          const int src = q0 - bb + slot;
           const int e = q0 + slot;
-          const float vf0 = __shfl_sync(0xffffffffu, v_l, src), vr0 = __shfl_sync(0xffffffffu, rv_l, src);
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f), q = f;
+          const float vf0 = __shfl_sync(0xffffffffu, v_l, src);
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
           const bool live = g_on && e < bend;
           if (live) {
             uint32_t code;
             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(st_base + src * 16 + g * 2));
-            const uint32_t addr = my_cb + code * 32 + ((code >> 2) & 1) * 16;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                          : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                         : "r"(addr));
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
-                         : "r"(addr ^ 16u));
+                         : "r"(my_cb + code * 128));
           }
           const int qend = min(q0 + EPS, bend);
           int j0 = q0;
           while (j0 < qend) {   // pieces of this sub-step that belong to one row
             const int pend = min(re, qend);
             const bool on = live && e >= j0 && e < pend;
-            const float vf = on ? vf0 : 0.f, vr = on ? vr0 : 0.f;
+            const float vf = on ? vf0 : 0.f;
             acc[0] = fmaf(vf, f.x, acc[0]), acc[1] = fmaf(vf, f.y, acc[1]), acc[2] = fmaf(vf, f.z, acc[2]), acc[3] = fmaf(vf, f.w, acc[3]);
-            acc[4] = fmaf(vr, q.x, acc[4]), acc[5] = fmaf(vr, q.y, acc[5]), acc[6] = fmaf(vr, q.z, acc[6]), acc[7] = fmaf(vr, q.w, acc[7]);
             pending = true;
             j0 = pend;
             if (pend == re) {  // row r complete
@@ -363,7 +356,7 @@ extern "C" int vqgnn_codes_apply_updates(const int32_t* nodes, const int16_t* ne
   VQ_CHECK_ARG(nodes && new_codes && codes && owner_ws && n >= 0 && n < (1ll << 31) && nbc > 0 && k0 >= 0 &&
                    k0 + nbc <= nb && N > 0,
                "codes_apply_updates: bad arguments");
-  VQ_CHECK_ARG(!codes_g || G == 6 || G == 8, "codes_apply_updates: bad group size");
+  VQ_CHECK_ARG(!codes_g || (G >= 1 && G <= 8), "codes_apply_updates: bad group size");
   if (n == 0) return VQGNN_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int g1 = static_cast<int>(std::min<int64_t>((n + 255) / 256, 8 * kNumSMs));
@@ -379,14 +372,13 @@ extern "C" int vqgnn_codes_apply_updates(const int32_t* nodes, const int16_t* ne
 
 extern "C" int vqgnn_mp_tail_group(int M, int D, int Wp) {
   if (D != 4 || Wp != 8 || M <= 0) return 0;
-  if (M * 32 * 8 <= 196608) return 8;
-  if (M * 32 * 6 <= 196608) return 6;
+  if (M * 128 <= 196608) return kTailG;   // one HALF of 8 branches' codebooks per pass: M * 8 * 16 B
   return 0;
 }
 
 extern "C" int vqgnn_codes_group(const int16_t* codes, int nb, const int32_t* rows, int64_t n_rows, int64_t N,
                                  int G, int16_t* codes_g, void* stream) {
-  VQ_CHECK_ARG(codes && codes_g && nb > 0 && n_rows >= 0 && N > 0 && (G == 6 || G == 8), "codes_group: bad arguments");
+  VQ_CHECK_ARG(codes && codes_g && nb > 0 && n_rows >= 0 && N > 0 && G >= 1 && G <= 8, "codes_group: bad arguments");
   if (n_rows == 0) return VQGNN_OK;
   const int grid = static_cast<int>(std::min<int64_t>((n_rows * nb + 255) / 256, 16 * kNumSMs));
   codes_group_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, nb, rows, n_rows, N, G, codes_g);
@@ -442,21 +434,14 @@ extern "C" int vqgnn_mp_fwd_tail(const int32_t* rowptr, const int32_t* node, con
   const int ng = (nb + G - 1) / G;
   // items = (group, block of cpi chunks): ~8 items per CTA, dealt round-robin
   const int grid = kNumSMs;
-  int items_per_group = std::max(1, (grid * 8 + ng - 1) / ng);
+  int items_per_group = std::max(1, (grid * 8 + 2 * ng - 1) / (2 * ng));   // per HALF group
   int cpi = std::max(kTailWarps, (n_chunks + items_per_group - 1) / items_per_group);
   items_per_group = (n_chunks + cpi - 1) / cpi;
-  const size_t smem = static_cast<size_t>(G) * M * 32 + 128;
-#define VQ_TAIL(GG)                                                                                           \
-  do {                                                                                                        \
-    auto kern = mp_tail_smem_kernel<GG>;                                                                      \
-    VQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-    kern<<<std::min(grid, ng * items_per_group), kTailThreads, smem, s>>>(                                    \
-        rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, d_nnz, (int)B, codes_g, N, O, nb, M,   \
-        feat_scale, yt, (int64_t)C, gq, ldgq, py, pgq, C, ng, cpi, items_per_group);                          \
-  } while (0)
-  if (G == 8) VQ_TAIL(8);
-  else VQ_TAIL(6);
-#undef VQ_TAIL
+  const size_t smem = static_cast<size_t>(M) * 128 + 128;
+  VQ_CUDA(cudaFuncSetAttribute(mp_tail_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mp_tail_smem_kernel<<<std::min(grid, 2 * ng * items_per_group), kTailThreads, smem, s>>>(
+      rowptr, node, val, rval, chunk_row, n_chunks, chunk, (int)nnz, d_nnz, (int)B, codes_g, N, O, nb, M, feat_scale, yt,
+      (int64_t)C, gq, ldgq, py, pgq, C, ng, cpi, items_per_group);
   VQ_LAUNCH_CHECK();
   const int64_t fx = static_cast<int64_t>(n_chunks) * (C / 2);
   mp_tail_fixup_kernel<<<static_cast<int>(std::min<int64_t>((fx + 255) / 256, 8 * kNumSMs)), 256, 0, s>>>(
