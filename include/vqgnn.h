@@ -173,6 +173,20 @@ int vqgnn_tail_materialize(const int32_t* tail_node, int64_t T, const int16_t* c
                            int M, int D, int Wp, float* tail_feat, float* tail_grad, int64_t ld_tail,
                            void* stream);
 
+/* info_backward of the v2 formulation over the out-of-batch rows only (csrc/mp_info.cu): the entries [e_begin, nnz) of
+ * the plan's CSR are those of rows r >= B (e_begin = rowptr[B]);
+ *   *info = info_scale * sum_e val[e] * < Xin[col[e], :], Gq[row(e), :] >          (vq_gnn_v2/models.py:198)
+ * with Xin = x for batch columns and the slab-major feature table tfS otherwise, Gq from the slab-major gradient
+ * table tgS.  vqgnn_tail_materialize_slab fills tfS / tgS [ceil(C / slab)][T][slab] (zero padded; slab in
+ * {16, 32, 64} columns): processed slab by slab the gathered slice stays L2-resident.  Pair it with vqgnn_mp_fwd over
+ * the first B rows (R = B, nnz = rowptr[B], info = NULL) for y.  ws: vqgnn_mp_info_workspace_bytes(nnz, C, slab). */
+int vqgnn_tail_materialize_slab(const int32_t* tail_node, int64_t T, const int16_t* codes, const float* O, int nb,
+                                int M, int D, int Wp, int slab, float* tfS, float* tgS, void* stream);
+size_t vqgnn_mp_info_workspace_bytes(int64_t nnz, int C, int slab);
+int vqgnn_mp_info(const int32_t* rowptr, const int32_t* col, const float* val, int64_t e_begin, int64_t nnz,
+                  int64_t B, int64_t R, const float* x, int64_t ldx, const float* tfS, const float* tgS, int C,
+                  int slab, float info_scale, float* info, void* ws, void* stream);
+
 /* Backward of the same: for batch column j < B
  *   dx[j, :] = sum_e bval[e] * (brow[e] < B ? dy[brow[e], :]
  *                                           : tail_scale * (*dinfo) * O_k[code(node(brow[e]-B), k), D:2D])
@@ -188,8 +202,10 @@ int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
 /* Out-of-batch ("tail") part of the forward with the codebooks of a branch group resident in shared
  * memory (csrc/mp_tail.cu) -- the fast path for the v1 formulation, where every batch row has hundreds of
  * out-of-batch neighbours (vq_gnn_v1/utils/dataloader.py:149-154 + vq_gnn_v1/models.py:181-223).
- *   vqgnn_mp_tail_group(M, D, Wp): branches per group G (8 or 6), or 0 if the shape is not supported
- *                                  (needs D == 4, Wp == 8, G*M*32 B <= 192 KB).
+ *   vqgnn_mp_tail_group(M, D, Wp): branches per group G (8), or 0 if the shape is not supported
+ *                                  (needs D == 4, Wp == 8, M*128 B <= 192 KB: one HALF -- feature or gradient
+ *                                  columns -- of 8 branches' codebooks per pass, stored so that the eight lanes of a
+ *                                  shared-memory load phase hit eight different bank groups: conflict-free gathers).
  *   vqgnn_codes_group: codes_g[(k/G)*N + node][k%G] = codes[node, k]  (codes_g: [ceil(nb/G)][N][8] int16) for
  *                      the listed nodes (rows == NULL: all N) -- the group-major mirror of the code table.
  *   vqgnn_mp_fwd_tail: over a CSR holding ONLY tail entries (node = global node id):

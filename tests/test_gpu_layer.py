@@ -384,3 +384,26 @@ def test_side_stream_vq_updates_are_bit_identical(version, conv):
     assert l0 == l1
     for k in s0:
         assert torch.equal(s0[k], s1[k]), k
+
+
+@pytest.mark.parametrize("conv,C,slab", [("GCN", 8, 16), ("SAGE", 52, 16), ("GCN", 128, 32), ("GCN", 100, 64)])
+def test_v2_split_info_kernel(conv, C, slab, monkeypatch):
+    """v2 training with the out-of-batch rows routed through csrc/mp_info.cu (slab-major tables, SDDMM-shaped
+    info_backward) and the batch rows through the generic kernel: same outputs / info / gradients / state as the
+    oracle; power-law graph (hub rows, empty rows), C not a multiple of the slab."""
+    from vq_gnn_b200 import models as Mo
+    monkeypatch.setattr(Mo, "INFO_SLAB", slab)
+    dev = torch.device("cuda:0")
+    N, B, M, D = 1500, 200, 32, 4
+    g = H.make_graph(N, 30_000, conv, "v2", seed=33, power_law=1.4)
+    batch_A = H.make_batch(g, B, "v2", seed=33)
+    torch.manual_seed(17)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, 6, M, D, N, conv), version="v2")
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, 6, M, D, N, conv, "v2", warm_up_flag=True).load_state_dict(sd)
+    layer = layer.to(dev)
+    layer.split_info = 'force'
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    c_outs = _run_cuda(layer, batch_A, x, 3, dev, wu=0.8)
+    _compare(c_outs, _run_oracle(o, batch_A, x, 3, wu=0.8, cuda_outs=c_outs), layer, o)
+    assert abs(float(c_outs[-1][1])) > 0

@@ -56,6 +56,9 @@ _SIGNATURES = {
     "vqgnn_plan_v1_workspace_bytes": (C.c_size_t, [i64, i64, i64, i64]),
     "vqgnn_plan_v1_build": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "vqgnn_tail_materialize_slab": (C.c_int, [vp, i64, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "vqgnn_mp_info_workspace_bytes": (C.c_size_t, [i64, i32, i32]),
+    "vqgnn_mp_info": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, vp, i32, i32, f32, vp, vp, vp]),
     "vqgnn_khop_workspace_bytes": (C.c_size_t, [i64, i64]),
     "vqgnn_khop_mark": (C.c_int, [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp]),
     "vqgnn_khop_count": (C.c_int, [vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]),
@@ -133,7 +136,8 @@ class _Proxy:
 _NO_STREAM = {"vqgnn_abi_version", "vqgnn_arch_check", "vqgnn_last_error", "vqgnn_launch_count",
               "vqgnn_mp_workspace_bytes", "vqgnn_mp_fwd_tail_workspace_bytes", "vqgnn_mp_num_chunks", "vqgnn_vq_assign_workspace_bytes", "vqgnn_mp_tail_group",
               "vqgnn_plan_v1_workspace_bytes", "vqgnn_csr_transpose_workspace_bytes",
-              "vqgnn_vq_moments_workspace_bytes", "vqgnn_vq_segsum_workspace_bytes", "vqgnn_khop_workspace_bytes"}
+              "vqgnn_vq_moments_workspace_bytes", "vqgnn_vq_segsum_workspace_bytes", "vqgnn_khop_workspace_bytes",
+              "vqgnn_mp_info_workspace_bytes"}
 
 
 def load():

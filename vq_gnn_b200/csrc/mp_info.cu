@@ -1,0 +1,185 @@
+// info_backward of the v2 ("B+B'") formulation over the OUT-OF-BATCH rows of the batch graph
+// (vq_gnn_v2/models.py:198):   info = wu * sum_{r >= B} < Y[r, :], Gq[r, :] >,   Y[r] = sum_e val[e] * Xin[col[e]]
+//   = wu * sum over the entries e of rows r >= B of  val[e] * < Xin[col[e], :], Gq[r, :] >        (an SDDMM-shaped sum)
+// with Xin[c] = x[c] for batch columns and the feature codewords F[c - B] of the out-of-batch node otherwise, and
+// Gq[r] the gradient codewords of node r.  These rows are ~95 % of the entries of a products-shaped batch graph
+// (B = 20 K batch nodes drag in ~10^6 one-hop neighbours and every edge among them) but only feed this scalar, so
+// nothing is written per row: every entry contributes one partial dot product.
+//
+// What bounds it: one gather of C floats per entry.  Read from a row-major [T, C] table (460 MB at the products
+// shape) almost every gather misses the 126 MB L2 and the kernel runs at HBM speed on 40x the compulsory bytes.
+// Here the gathered tables are SLAB-MAJOR, tfS / tgS [ceil(C / SLAB)][T][SLAB], and the work is ordered slab by slab:
+// while a slab is processed its slice (T * SLAB * 4 B = 58 MB at SLAB = 16) is L2-resident, so the gathers are L2
+// hits and HBM only streams the edge list once per slab.  Lane = (entry slot, 4 columns of the slab); a slot owns
+// 32 CONSECUTIVE entries, so it re-reads Gq only when its row changes and loads col / val as 128-bit vectors.
+// Deterministic: static work assignment, per-block partials added in block order (info_reduce_ordered).
+#include "mp_common.cuh"
+
+namespace vqgnn {
+
+constexpr int kInfoRun = 32;   // consecutive entries per slot
+
+template <int SLAB>
+__global__ void __launch_bounds__(kMpWarps * 32)
+    mp_info_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                   const float* __restrict__ val, int64_t e_begin, int64_t nnz, int B, int R, int64_t T,
+                   const float* __restrict__ x, int64_t ldx, const float* __restrict__ tfS,
+                   const float* __restrict__ tgS, int C, int nslab, int64_t n_etasks, float info_scale,
+                   float* __restrict__ info, double* ws_part, unsigned int* ws_count) {
+  constexpr int LPE = SLAB / 4;          // lanes per entry
+  constexpr int SLOTS = 32 / LPE;        // entry slots per warp
+  constexpr int EPT = SLOTS * kInfoRun;  // entries per warp task
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
+  float fpart = 0.f;
+  if (task < n_etasks * nslab) {
+    const int slab = static_cast<int>(task / n_etasks);      // slab-major: concurrently running CTAs share a slab
+    const int64_t et = task - static_cast<int64_t>(slab) * n_etasks;
+    const int slot = lane / LPE, cg = lane - slot * LPE;
+    const int colbase = slab * SLAB + cg * 4;
+    const int64_t a0 = e_begin & ~static_cast<int64_t>(3);
+    const int64_t es = a0 + et * EPT + static_cast<int64_t>(slot) * kInfoRun;
+    const int64_t first = max(es, e_begin), last = min(es + kInfoRun, nnz);
+    if (first < last) {
+      const float* tf = tfS + static_cast<int64_t>(slab) * T * SLAB + cg * 4;
+      const float* tg = tgS + static_cast<int64_t>(slab) * T * SLAB + cg * 4;
+      // row of the first entry: largest r in [B, R) with rowptr[r] <= first
+      int lo = B, hi = R;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(rowptr + mid) <= first) lo = mid;
+        else hi = mid;
+      }
+      int r = lo;
+      int64_t re = __ldg(rowptr + r + 1);
+      float4 gv = __ldg(reinterpret_cast<const float4*>(tg + static_cast<int64_t>(r - B) * SLAB));
+#pragma unroll 2
+      for (int64_t e = es; e < last; e += 4) {
+        int c[4];
+        float v[4];
+        if (e + 4 <= nnz) {
+          const int4 cc = __ldg(reinterpret_cast<const int4*>(col + e));
+          const float4 vv = __ldg(reinterpret_cast<const float4*>(val + e));
+          c[0] = cc.x, c[1] = cc.y, c[2] = cc.z, c[3] = cc.w;
+          v[0] = vv.x, v[1] = vv.y, v[2] = vv.z, v[3] = vv.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            c[u] = e + u < nnz ? __ldg(col + e + u) : 0;
+            v[u] = e + u < nnz ? __ldg(val + e + u) : 0.f;
+          }
+        }
+        float4 xin[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // the gathers: all four in flight
+          const bool ok = e + u >= first && e + u < last;
+          xin[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            if (c[u] >= B) xin[u] = __ldg(reinterpret_cast<const float4*>(tf + static_cast<int64_t>(c[u] - B) * SLAB));
+            else if (colbase < C) xin[u] = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(c[u]) * ldx + colbase));
+          } else {
+            v[u] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (e + u >= re && e + u < last) {   // the slot's row changed (rows may be empty)
+            do {
+              ++r;
+              re = __ldg(rowptr + r + 1);
+            } while (e + u >= re);
+            gv = __ldg(reinterpret_cast<const float4*>(tg + static_cast<int64_t>(r - B) * SLAB));
+          }
+          const float d = fmaf(xin[u].x, gv.x, fmaf(xin[u].y, gv.y, fmaf(xin[u].z, gv.z, xin[u].w * gv.w)));
+          fpart = fmaf(v[u], d, fpart);
+        }
+      }
+    }
+  }
+  info_reduce_ordered(static_cast<double>(fpart), ws_part, ws_count, info_scale, info);
+}
+
+// slab-major copies of the tail entries' codewords (D == 4, Wp == 8): warp per tail entry, lane = branch
+__global__ void __launch_bounds__(256)
+    tail_materialize_slab_kernel(const int32_t* __restrict__ tail_node, int64_t T, const int16_t* __restrict__ codes,
+                                 const float* __restrict__ O, int nb, int M, int slab, int nslab,
+                                 float* __restrict__ tfS, float* __restrict__ tgS) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (t >= T) return;
+  const int64_t node = tail_node ? __ldg(tail_node + t) : t;
+  const int nq = nslab * slab / 4;   // 4-column groups incl. the zero padding of the last slab
+  for (int k = lane; k < nq; k += 32) {
+    float f[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k < nb) {
+      const int code = __ldg(codes + node * nb + k);
+      ld_sector(O + (static_cast<int64_t>(k) * M + code) * 8, f, g);
+    }
+    const int c0 = 4 * k, s = c0 / slab, o = c0 - s * slab;
+    const int64_t off = (static_cast<int64_t>(s) * T + t) * slab + o;
+    if (tfS) st_vec<4>(tfS + off, f);
+    if (tgS) st_vec<4>(tgS + off, g);
+  }
+}
+
+}  // namespace vqgnn
+
+using namespace vqgnn;
+
+extern "C" int vqgnn_tail_materialize_slab(const int32_t* tail_node, int64_t T, const int16_t* codes, const float* O,
+                                           int nb, int M, int D, int Wp, int slab, float* tfS, float* tgS,
+                                           void* stream) {
+  VQ_CHECK_ARG(codes && O && T >= 0 && nb > 0 && (tfS || tgS), "tail_materialize_slab: bad arguments");
+  VQ_CHECK_ARG(D == 4 && Wp == 8 && aligned32(O) && (slab == 16 || slab == 32 || slab == 64) &&
+                   (!tfS || aligned16(tfS)) && (!tgS || aligned16(tgS)),
+               "tail_materialize_slab: needs D == 4, Wp == 8, slab in {16, 32, 64} and 16 B aligned outputs");
+  if (T == 0) return VQGNN_OK;
+  const int nslab = ceil_div(nb * 4, slab);
+  tail_materialize_slab_kernel<<<ceil_div(T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      tail_node, T, codes, O, nb, M, slab, nslab, tfS, tgS);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}
+
+extern "C" size_t vqgnn_mp_info_workspace_bytes(int64_t nnz, int C, int slab) {
+  const int nslab = (C + slab - 1) / slab;
+  const int64_t ept = static_cast<int64_t>(32 / (slab / 4)) * kInfoRun;
+  const int64_t tasks = ((nnz + 3 + ept - 1) / ept + 1) * nslab;
+  return 512 + static_cast<size_t>((tasks + kMpWarps - 1) / kMpWarps + 1) * 8;
+}
+
+extern "C" int vqgnn_mp_info(const int32_t* rowptr, const int32_t* col, const float* val, int64_t e_begin, int64_t nnz,
+                             int64_t B, int64_t R, const float* x, int64_t ldx, const float* tfS, const float* tgS,
+                             int C, int slab, float info_scale, float* info, void* ws, void* stream) {
+  VQ_CHECK_ARG(rowptr && col && val && x && tfS && tgS && info && ws, "mp_info: null argument");
+  VQ_CHECK_ARG(B > 0 && R >= B && R < (1ll << 31) && e_begin >= 0 && e_begin <= nnz && nnz < (1ll << 31) && C > 0,
+               "mp_info: bad sizes");
+  VQ_CHECK_ARG((slab == 16 || slab == 32 || slab == 64) && ldx % 4 == 0 && C % 4 == 0 && aligned16(x) &&
+                   aligned16(tfS) && aligned16(tgS) && aligned16(col) && aligned16(val),
+               "mp_info: slab must be 16 / 32 / 64 and every operand 16 B aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (R == B || e_begin == nnz) {
+    VQ_CUDA(cudaMemsetAsync(info, 0, sizeof(float), s));
+    return VQGNN_OK;
+  }
+  const int nslab = ceil_div(C, slab);
+  const int64_t ept = static_cast<int64_t>(32 / (slab / 4)) * kInfoRun;
+  const int64_t a0 = e_begin & ~static_cast<int64_t>(3);
+  const int64_t n_etasks = (nnz - a0 + ept - 1) / ept;
+  const int64_t tasks = n_etasks * nslab;
+  const int grid = static_cast<int>((tasks + kMpWarps - 1) / kMpWarps);
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
+  unsigned int* ws_count = reinterpret_cast<unsigned int*>(p);
+  double* ws_part = reinterpret_cast<double*>(p + 256);
+  VQ_CUDA(cudaMemsetAsync(ws_count, 0, 16, s));
+  const int64_t T = R - B;
+#define VQ_INFO(SL)                                                                                              \
+  mp_info_kernel<SL><<<grid, kMpWarps * 32, 0, s>>>(rowptr, col, val, e_begin, nnz, (int)B, (int)R, T, x, ldx, tfS, \
+                                                    tgS, C, nslab, n_etasks, info_scale, info, ws_part, ws_count)
+  if (slab == 16) VQ_INFO(16);
+  else if (slab == 32) VQ_INFO(32);
+  else VQ_INFO(64);
+#undef VQ_INFO
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}

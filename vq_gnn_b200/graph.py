@@ -141,6 +141,14 @@ class BatchPlan:
     fwd_rval = property(lambda self: self._merged()[3])     # fp32  [nnz] reverse values (v1) or None
 
     @property
+    def nnz_B(self) -> int:
+        """Entries of the first B rows of the forward CSR (v2: the batch rows; rows >= B only feed info_backward)."""
+        n = self.extras.get('nnz_B')
+        if n is None:
+            n = self.extras['nnz_B'] = int(self.fwd_rowptr[self.B])
+        return n
+
+    @property
     def has_rval(self) -> bool:
         return self._has_rval if self._has_rval is not None else self.fwd_rval is not None
 
@@ -182,9 +190,11 @@ class BatchPlan:
             if which == 'fwd':
                 rowptr = self.fwd_rowptr          # materialises a lazy merged CSR (and makes nnz exact) first
                 nnz, rows = self.nnz, self.R
+            elif which == 'fwdB':                 # the batch rows only (v2 split forward)
+                rowptr, nnz, rows = self.fwd_rowptr, self.nnz_B, self.B
             else:
                 rowptr, nnz, rows = self.bwd_rowptr, int(self.bwd_col.numel()), self.B
-            chunk = MP_CHUNK if which == 'fwd' else self.small_chunk
+            chunk = MP_CHUNK if which in ('fwd', 'fwdB') else self.small_chunk
             _lib.require_device(rowptr)
             lib = _lib.load()
             n = int(lib.vqgnn_mp_num_chunks(nnz, chunk))
@@ -514,6 +524,8 @@ def plan_from_graph_v2(g, node_idx: Tensor, conv_type: str, training: bool = Tru
     _lib.check(lib.vqgnn_khop_count(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(ids), _lib.ptr(tail_node), B, R, N,
                                     _lib.ptr(out_rowptr), _lib.ptr(cnt[1:]), _lib.ptr(ws), st))
     host[1:].copy_(cnt[1:], non_blocking=True)
+    host_b = _pinned_i32(1)
+    host_b.copy_(out_rowptr[B:B + 1], non_blocking=True)
     torch.cuda.current_stream().synchronize()
     nnz = int(host[1])
     out_col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
@@ -542,7 +554,8 @@ def plan_from_graph_v2(g, node_idx: Tensor, conv_type: str, training: bool = Tru
         return browptr, brow[:n], bval[:n]
 
     return BatchPlan('v2', conv_type, B, R, T, N, bidx, out_rowptr, out_col, out_val, None, tail_node, None, None,
-                     None, None, training, extras={'_keep': (ws, tws, count, brow, bval, browptr, tail_all, ids)},
+                     None, None, training,
+                     extras={'_keep': (ws, tws, count, brow, bval, browptr, tail_all, ids), 'nnz_B': int(host_b[0])},
                      bwd_builder=bwd)
 
 

@@ -26,6 +26,10 @@ from torch import nn
 from . import _lib
 from .convs import OurGATConv, OurGCNConv
 from .graph import MP_CHUNK, TAIL_CHUNK, TAIL_MIN_AVG_DEGREE, BatchPlan, CSRAdj, build_plan
+
+import os as _os
+INFO_SLAB = int(_os.environ.get('VQGNN_INFO_SLAB', '16'))     # columns per slab of the split info kernel (16/32/64)
+INFO_SPLIT_MIN_ENTRIES = 1 << 20     # below this the one-kernel forward is as fast
 from .vq import VectorQuantizerEMA, VQBank
 
 Tensor = torch.Tensor
@@ -97,6 +101,30 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(tcount), B, _lib.ptr(x), x.stride(0), _lib.ptr(codes_g), codes_g.shape[1], _lib.ptr(bank.O), bank.nb,
                 bank.M, bank.D, bank.Wp, float(wu), float(wu), _lib.ptr(y), y.stride(0), _lib.ptr(gq),
                 gq.stride(0), _lib.ptr(info) if need_info else None, _lib.ptr(ws), st))
+        elif (not v1 and need_info and plan.T > 0 and bank.D == 4 and bank.Wp == 8 and layer.split_info
+              and (layer.split_info == 'force' or plan.nnz - plan.nnz_B >= INFO_SPLIT_MIN_ENTRIES)):
+            # v2 training, large batch graph: the rows >= B (most of the entries) only feed the info_backward scalar.
+            # Batch rows through the generic kernel (y), the rest through the slab-ordered SDDMM-shaped kernel whose
+            # gathers stay L2-resident (csrc/mp_info.cu).
+            slab = INFO_SLAB
+            nslab = (C + slab - 1) // slab
+            tfS = torch.empty(nslab, plan.T, slab, device=dev)
+            tgS = torch.empty(nslab, plan.T, slab, device=dev)
+            _lib.check(lib.vqgnn_tail_materialize_slab(
+                _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
+                bank.Wp, slab, _lib.ptr(tfS), _lib.ptr(tgS), st))
+            nB = plan.nnz_B
+            _lib.check(lib.vqgnn_mp_fwd(
+                _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), None,
+                _lib.ptr(plan.chunk_rows('fwdB')), MP_CHUNK, nB, B, B, _lib.ptr(x), x.stride(0),
+                _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
+                None, 0, 1.0, float(wu), _lib.ptr(y), y.stride(0), None, 0, None,
+                _lib.ptr(_mp_ws(dev, nB, MP_CHUNK, C)), st))
+            iws = torch.empty(int(lib.vqgnn_mp_info_workspace_bytes(plan.nnz, C, slab)), dtype=torch.uint8, device=dev)
+            _lib.check(lib.vqgnn_mp_info(
+                _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), nB, plan.nnz, B, plan.R,
+                _lib.ptr(x), x.stride(0), _lib.ptr(tfS), _lib.ptr(tgS), C, slab, float(wu), _lib.ptr(info),
+                _lib.ptr(iws), st))
         else:
             tail_feat = None
             auto = plan.nnz >= 4 * plan.T      # tail nodes referenced several times each: gather once, read dense
@@ -310,6 +338,9 @@ class LowRankGNNLayer(nn.Module):
         # True = when tail nodes are referenced >= 4x on average (measured per layer: arxiv 1.61 -> 1.50 ms, collab
         # 1.59 -> 1.49, products forward 2.09 -> 1.17 + 0.18 ms), 'force' = always, False = never
         self.materialize_tail = True
+        # v2 training: batch rows and out-of-batch rows (info_backward only) through separate kernels when the latter
+        # hold >= INFO_SPLIT_MIN_ENTRIES entries (csrc/mp_info.cu); 'force' = always, False = never
+        self.split_info = True
         self._restack()
 
     # ---- stacked storage <-> per-branch reference buffers -------------------------------------
