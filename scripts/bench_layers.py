@@ -53,17 +53,11 @@ def make_case(name, dev):
 
 
 def algorithmic_bytes(kernel, plan, bank, B, C):
-    nb, M = bank.nb, bank.M
-    nnz = plan.nnz
-    tail = int((plan.fwd_col >= B).sum())
-    R = plan.R
-    if kernel in ("vqgnn_mp_fwd", "vqgnn_gat_fwd", "vqgnn_mp_fwd_tail"):
-        return tail * (8 + 2 * nb) + (nnz - tail) * 8 + (R + 1) * 4 + 2 * B * C * 4 + (R - B) * nb * 2 + 2 * M * C * 4
-    if kernel in ("vqgnn_mp_bwd", "vqgnn_gat_bwd"):
-        return int(plan.bwd_col.numel()) * 8 + 3 * B * C * 4 + M * C * 4 + (nnz * 8 if "gat" in kernel else 0)
-    if kernel == "vqgnn_vq_moments":
-        return 2 * B * C * 4
-    return None
+    """Per-kernel compulsory bytes, the same function bench.py uses for its roofline -- one
+    formula per kernel (round 1 applied the full-forward formula to the in-batch-only launch and reported frac > 1)."""
+    import bench
+    work, bound = bench.algorithmic_work(kernel, plan, C, bank.nb, bank.M, B)
+    return work if (bound == "hbm" and work) else None
 
 
 def main():

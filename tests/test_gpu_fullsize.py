@@ -163,3 +163,36 @@ def test_c5_products_shape_v2_gcn():
     _warm(layer, x, plan, steps=1)
     _vq_properties(layer, x, plan)
     _check_conv(layer, x, plan, 1.0, R.gcn_v2)
+
+
+def test_c4_collab_shape_v2_gcn_link():
+    """configs[3]: the layer op at the collab shape (integer edge weights kept as values, power-law degrees, cont
+    sampler batch of 50000) + one link-prediction train step through LinkPredictor (positive edges = in-batch edges)."""
+    from vq_gnn_b200 import link
+    dev = torch.device("cuda:0")
+    s = synth.CONFIG_SHAPES["c4_collab"]
+    N = s["N"]
+    rowptr, row, col = synth.random_edges(N, s["E"], seed=0, power_law=s["power_law"], device=dev)
+    lo_, hi_ = torch.minimum(row, col), torch.maximum(row, col)
+    w = ((lo_ * 2654435761 + hi_ * 40503) % 3 + 1).float()
+    g = synth.normalized_graph(N, rowptr, row, col, "GCN", "v2", edge_weight=w)
+    gen = torch.Generator(device=dev).manual_seed(6)
+    seeds = torch.randperm(N, generator=gen, device=dev)[:50000]
+    nodes = sampling.cont_sampler(g, seeds, 15, 50000, generator=gen)[4]
+    layer = _layer(128, 128, 1024, N, "GCN", "v2", dev, skip=True)
+    plan = V.graph.plan_from_graph_v2(g, nodes, "GCN", True).warm()
+    x = torch.randn(nodes.numel(), 128, device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    _warm(layer, x, plan)
+    _vq_properties(layer, x, plan)
+    _check_conv(layer, x, plan, 1.0, R.gcn_v2)
+    # one link-prediction step: finite loss, gradients reach the layer and the predictor
+    torch.manual_seed(1)
+    pred = link.LinkPredictor(128, 128, 1, 3, 0.0).to(dev)
+    src, dst = link.positive_edges(plan)
+    assert src.numel() > 0 and int(src.max()) < plan.B and int(dst.max()) < plan.B
+    xx = x.clone().requires_grad_(True)
+    out = layer(xx, plan, 1.0, False)
+    loss = link.link_loss(pred, out[0], plan) + out[5]
+    loss.backward()
+    assert torch.isfinite(loss) and float(xx.grad.abs().sum()) > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in pred.parameters())

@@ -136,3 +136,33 @@ def test_k_hop_batch_matches_the_reference_loader(train):
     k0, v0 = triples(subset, row, col, val)
     k1, v1 = triples(subset_r, ei_r[0], ei_r[1], w_r)
     assert torch.equal(k0, k1) and torch.equal(v0, v1)
+
+
+def test_link_head_matches_main_link():
+    """vq_gnn_b200.link: positive edges = the batch graph's edges with both ends among the batch nodes
+    (vq_gnn_v2/utils/misc.py:87-88); loss = -log(p_pos + 1e-15).mean() - log(1 - p_neg + 1e-15).mean() with
+    p = sigmoid(MLP(x_i * x_j)) (main_link.py:18-41, 57-66), restated literally here."""
+    import torch.nn.functional as F
+    from vq_gnn_b200 import link, sampling
+    N, B = 400, 70
+    g = H.make_graph(N, 3000, "GCN", "v2", seed=12)
+    nodes = torch.randperm(N, generator=torch.Generator().manual_seed(2))[:B]
+    bA = sampling.k_hop_batch_v2(g, nodes, True)
+    src, dst = link.positive_edges(bA)
+    row, col, _ = bA[2].coo()
+    mask = (row < B) & (col < B)
+    assert torch.equal(src, row[mask]) and torch.equal(dst, col[mask]) and src.numel() > 0
+    torch.manual_seed(0)
+    pred = link.LinkPredictor(16, 12, 1, 3, 0.0)
+    assert [tuple(l.weight.shape) for l in pred.lins] == [(12, 16), (12, 12), (1, 12)]
+    out = torch.randn(B, 16)
+    dst_neg = torch.randint(0, B, src.shape, generator=torch.Generator().manual_seed(4))
+
+    def p(xi, xj):
+        h = xi * xj
+        for lin in pred.lins[:-1]:
+            h = F.relu(lin(h))
+        return torch.sigmoid(pred.lins[-1](h))
+    want = -torch.log(p(out[src], out[dst]) + 1e-15).mean() - torch.log(1 - p(out[src], out[dst_neg]) + 1e-15).mean()
+    got = link.link_loss(pred, out, bA, dst_neg=dst_neg)
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
