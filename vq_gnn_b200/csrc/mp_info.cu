@@ -19,6 +19,34 @@ namespace vqgnn {
 
 constexpr int kInfoRun = 32;   // consecutive entries per slot
 
+// L2 residency control: the edge list and the per-row gradient slices are STREAMED (each byte used once per slab) and
+// together exceed the slice of the feature table that must stay resident, so they are loaded evict-first while the
+// gathered feature rows are loaded evict-last.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int4 ldg_i4_hint(const int32_t* p, uint64_t pol) {
+  int4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+
 template <int SLAB>
 __global__ void __launch_bounds__(kMpWarps * 32)
     mp_info_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -32,6 +60,7 @@ __global__ void __launch_bounds__(kMpWarps * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t task = static_cast<int64_t>(blockIdx.x) * kMpWarps + warp;
   float fpart = 0.f;
+  const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
   if (task < n_etasks * nslab) {
     const int slab = static_cast<int>(task / n_etasks);      // slab-major: concurrently running CTAs share a slab
     const int64_t et = task - static_cast<int64_t>(slab) * n_etasks;
@@ -52,14 +81,14 @@ __global__ void __launch_bounds__(kMpWarps * 32)
       }
       int r = lo;
       int64_t re = __ldg(rowptr + r + 1);
-      float4 gv = __ldg(reinterpret_cast<const float4*>(tg + static_cast<int64_t>(r - B) * SLAB));
+      float4 gv = ldg_f4_hint(tg + static_cast<int64_t>(r - B) * SLAB, pol_stream);
 #pragma unroll 2
       for (int64_t e = es; e < last; e += 4) {
         int c[4];
         float v[4];
         if (e + 4 <= nnz) {
-          const int4 cc = __ldg(reinterpret_cast<const int4*>(col + e));
-          const float4 vv = __ldg(reinterpret_cast<const float4*>(val + e));
+          const int4 cc = ldg_i4_hint(col + e, pol_stream);
+          const float4 vv = ldg_f4_hint(val + e, pol_stream);
           c[0] = cc.x, c[1] = cc.y, c[2] = cc.z, c[3] = cc.w;
           v[0] = vv.x, v[1] = vv.y, v[2] = vv.z, v[3] = vv.w;
         } else {
@@ -75,8 +104,8 @@ __global__ void __launch_bounds__(kMpWarps * 32)
           const bool ok = e + u >= first && e + u < last;
           xin[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok) {
-            if (c[u] >= B) xin[u] = __ldg(reinterpret_cast<const float4*>(tf + static_cast<int64_t>(c[u] - B) * SLAB));
-            else if (colbase < C) xin[u] = __ldg(reinterpret_cast<const float4*>(x + static_cast<int64_t>(c[u]) * ldx + colbase));
+            if (c[u] >= B) xin[u] = ldg_f4_hint(tf + static_cast<int64_t>(c[u] - B) * SLAB, pol_keep);
+            else if (colbase < C) xin[u] = ldg_f4_hint(x + static_cast<int64_t>(c[u]) * ldx + colbase, pol_keep);
           } else {
             v[u] = 0.f;
           }
@@ -88,7 +117,7 @@ __global__ void __launch_bounds__(kMpWarps * 32)
               ++r;
               re = __ldg(rowptr + r + 1);
             } while (e + u >= re);
-            gv = __ldg(reinterpret_cast<const float4*>(tg + static_cast<int64_t>(r - B) * SLAB));
+            gv = ldg_f4_hint(tg + static_cast<int64_t>(r - B) * SLAB, pol_stream);
           }
           const float d = fmaf(xin[u].x, gv.x, fmaf(xin[u].y, gv.y, fmaf(xin[u].z, gv.z, xin[u].w * gv.w)));
           fpart = fmaf(v[u], d, fpart);
