@@ -119,6 +119,25 @@ def _worker(rank, world_size, port, tmp):
             want[idx_all[rr].long()] = new_all[rr]
         assert torch.equal(table, want) and gidx.numel() == world_size * Bc
         assert vdist.replicas_max_abs_diff(table.float()) == 0.0
+        # ---- ranks with DIFFERENT batch sizes: refused without a capacity, padded (node id -1) with one ----------
+        Bs = [5, 8]
+        idx_r = torch.randperm(Nn, generator=torch.Generator().manual_seed(20 + rank))[:Bs[rank]].to(torch.int32)
+        new_r = torch.randint(0, 99, (Bs[rank], nbr), generator=torch.Generator().manual_seed(30 + rank),
+                              dtype=torch.int16)
+        try:
+            vdist.allgather_code_updates(idx_r, new_r)
+            raise AssertionError("unequal batch sizes must be refused when no capacity is given")
+        except ValueError:
+            pass
+        t2 = torch.zeros(Nn, nbr, dtype=torch.int16)
+        gidx2 = vdist.allgather_code_updates_(t2, idx_r, new_r, capacity=8)
+        assert gidx2.numel() == world_size * 8 and int((gidx2 < 0).sum()) == 3
+        want2 = torch.zeros(Nn, nbr, dtype=torch.int16)
+        for rr in range(world_size):
+            ir = torch.randperm(Nn, generator=torch.Generator().manual_seed(20 + rr))[:Bs[rr]]
+            want2[ir] = torch.randint(0, 99, (Bs[rr], nbr), generator=torch.Generator().manual_seed(30 + rr),
+                                      dtype=torch.int16)
+        assert torch.equal(t2, want2) and vdist.replicas_max_abs_diff(t2.float()) == 0.0
         with open(os.path.join(tmp, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:

@@ -179,3 +179,38 @@ def test_prepare_from_graph_trains_like_the_host_batch():
                 assert torch.equal(s0[k], s1[k]), k
         else:                        # v2: the torch builder sorts a row by relabelled column, the device one keeps the
             assert l0 == pytest.approx(l1, rel=1e-5)        # graph's stored order -- same sums in a different order
+
+
+@pytest.mark.parametrize("version,conv", [("v2", "GCN"), ("v1", "SAGE"), ("v2", "GAT")])
+def test_streaming_warm_start_matches_per_batch_init(version, conv):
+    """LowRankGNN.warm_start (the reference's init(): L(L+1)/2 streaming layer passes over the whole graph with the
+    test loader's batch-rows-only batches, main_node.py:17-37) vs the same loop written with host-built batches."""
+    from vq_gnn_b200 import sampling
+    dev = torch.device("cuda:0")
+    N, M, C, bs = 900, 16, 8, 250
+    g = H.make_graph(N, 7000, conv, version, seed=5).to(dev)
+    X = torch.randn(N, C, generator=torch.Generator().manual_seed(1)).to(dev)
+
+    def build():
+        torch.manual_seed(0)
+        return V.LowRankGNN(C, 8, 5, 3, 0., M, 4, N, no_second_fc=True, skip=False, commitment_cost=0.,
+                            grad_scale=[1, 1], act='leaky_gelu', bn_flag=True, warm_up_flag=True, conv_type=conv,
+                            version=version).to(dev).train()
+    m0, m1 = build(), build()
+    n_b = m0.warm_start(g, X, bs)
+    assert n_b == (N + bs - 1) // bs and all(l.inited for l in m0.convs)
+    with torch.no_grad():
+        for layer_idx in range(1, 4):
+            for lo in range(0, N, bs):
+                ids = torch.arange(lo, min(lo + bs, N), device=dev)
+                bA = (sampling.k_hop_batch_v2(g, ids, train_flag=False) if version == "v2"
+                      else sampling.collate_batch_v1(g, ids, train_flag=False, recovery_flag=False))
+                plan = V.build_plan(bA, conv, N, False, dev)
+                plan.training = True          # the reference's init(): eval-structured batches, model in train mode
+                m1.init((X[ids], plan), layer_idx)
+    m1.set_inited(True)
+    sd0, sd1 = m0.state_dict(), m1.state_dict()
+    for k in sd0:
+        a, b = sd0[k].float(), sd1[k].float()
+        assert float((a - b).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-6), k
+    m0.check_status()

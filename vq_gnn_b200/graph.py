@@ -494,12 +494,16 @@ def _pinned_i32(n: int = 1) -> Tensor:
     return torch.empty(n, dtype=torch.int32).pin_memory()
 
 
-def plan_from_graph_v2(g, node_idx: Tensor, conv_type: str, training: bool = True) -> BatchPlan:
+def plan_from_graph_v2(g, node_idx: Tensor, conv_type: str, training: bool = True,
+                       batch_rows_only: bool = False) -> BatchPlan:
     """v2 batch plan straight from the device-resident graph `g` (rowptr int64, col / col32, val) and the batch's
     node ids: csrc/khop.cu restates `_k_hop_subgraph` + `prepare_batch_input` (vq_gnn_v2/dataloader.py:98-148,
     utils/misc.py:57-75) on the device -- subset = [batch ; ascending out-of-batch 1-hop neighbours], train keeps
     every edge inside the subset, eval the batch rows only -- and hands the relabelled int32 CSR to the kernels
-    without ever forming the reference's int64 COO.  Two small device->host reads (B' and nnz) size the outputs."""
+    without ever forming the reference's int64 COO.  Two small device->host reads (B' and nnz) size the outputs.
+    batch_rows_only: keep only the batch rows (the loader's train_flag=False structure) in a plan that is still
+    marked `training` -- what the reference's init() feeds a model in train mode (main_node.py:17-37 uses the
+    TEST loader)."""
     from . import _lib
     lib, st = _lib.load(), _lib.stream()
     dev = g.col.device
@@ -519,7 +523,7 @@ def plan_from_graph_v2(g, node_idx: Tensor, conv_type: str, training: bool = Tru
     torch.cuda.current_stream().synchronize()
     T = int(host[0])
     tail_node = tail_all[:T]
-    R = B + T if training else B
+    R = B + T if (training and not batch_rows_only) else B
     out_rowptr = torch.empty(R + 1, dtype=torch.int32, device=dev)
     _lib.check(lib.vqgnn_khop_count(_lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(ids), _lib.ptr(tail_node), B, R, N,
                                     _lib.ptr(out_rowptr), _lib.ptr(cnt[1:]), _lib.ptr(ws), st))

@@ -517,6 +517,35 @@ class LowRankGNN(nn.Module):
             x, _, _, _, _, _, _ = conv(x, batch_A, 1, False)
             x = self.act_f(x)
 
+    @torch.no_grad()
+    def warm_start(self, graph, X: Tensor, batch_size: int, node_order: Optional[Tensor] = None) -> int:
+        """The reference's `init(data, model, device, test_loader)` (vq_gnn_v2/main_node.py:17-37, v1 alike) as a
+        streaming pass over the device-resident graph: for layer_idx = 1..L, every node batch of the TEST loader
+        (consecutive ranges of `node_order`, batch rows only) runs `model.init(batch, layer_idx)` -- a feature-only
+        codebook update of each visited layer -- then every block is marked inited.  L(L+1)/2 layer passes over the
+        whole graph, all on the device: node ids never leave it.  Returns the number of batches per pass."""
+        from . import graph as G
+        was_training = self.training
+        self.train()
+        dev = graph.col.device
+        N = int(graph.N)
+        order = torch.arange(N, device=dev) if node_order is None else node_order.to(dev)
+        nb = 0
+        for layer_idx in range(1, self.num_layers + 1):
+            nb = 0
+            for lo in range(0, N, batch_size):
+                ids = order[lo:lo + batch_size]
+                if self.version == 'v2':
+                    plan = G.plan_from_graph_v2(graph, ids, self.conv_type, True, batch_rows_only=True)
+                else:
+                    bA = G.batch_from_graph_v1(graph, ids, train_flag=False, recovery_flag=False)
+                    plan = build_plan(bA, self.conv_type, self.num_N, True, dev)
+                self.init((X[ids], plan), layer_idx)
+                nb += 1
+        self.set_inited(True)
+        self.train(was_training)
+        return nb
+
     def set_inited(self, flag: bool = True):
         """What main's init() does after the warm-start passes (main_node.py:30-37)."""
         for layer in self.convs:
