@@ -531,6 +531,11 @@ class LowRankGNN(nn.Module):
         N = int(graph.N)
         order = torch.arange(N, device=dev) if node_order is None else node_order.to(dev)
         nb = 0
+        # every rank streams the WHOLE graph and (the update being deterministic) arrives at identical replicas:
+        # no collective is needed, and summing identical statistics over ranks would only rescale them
+        dist_flags = [layer.bank.distributed for layer in self.convs]
+        for layer in self.convs:
+            layer.bank.distributed = False
         for layer_idx in range(1, self.num_layers + 1):
             nb = 0
             for lo in range(0, N, batch_size):
@@ -542,6 +547,8 @@ class LowRankGNN(nn.Module):
                     plan = build_plan(bA, self.conv_type, self.num_N, True, dev)
                 self.init((X[ids], plan), layer_idx)
                 nb += 1
+        for layer, flag in zip(self.convs, dist_flags):
+            layer.bank.distributed = flag
         self.set_inited(True)
         self.train(was_training)
         return nb
