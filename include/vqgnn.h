@@ -174,7 +174,7 @@ int vqgnn_tail_materialize(const int32_t* tail_node, int64_t T, const int16_t* c
                            void* stream);
 
 /* info_backward of the v2 formulation over the out-of-batch rows only (csrc/mp_info.cu): the entries [e_begin, nnz) of
- * the plan's CSR are those of rows r >= B (e_begin = rowptr[B]);
+ * the plan's CSR are those of rows r >= B (e_begin = rowptr[B]; erow [nnz] holds their row ids, vqgnn_csr_expand_rows);
  *   *info = info_scale * sum_e val[e] * < Xin[col[e], :], Gq[row(e), :] >          (vq_gnn_v2/models.py:198)
  * with Xin = x for batch columns and the slab-major feature table tfS otherwise, Gq from the slab-major gradient
  * table tgS.  vqgnn_tail_materialize_slab fills tfS / tgS [ceil(C / slab)][T][slab] (zero padded; slab in
@@ -183,7 +183,9 @@ int vqgnn_tail_materialize(const int32_t* tail_node, int64_t T, const int16_t* c
 int vqgnn_tail_materialize_slab(const int32_t* tail_node, int64_t T, const int16_t* codes, const float* O, int nb,
                                 int M, int D, int Wp, int slab, float* tfS, float* tgS, void* stream);
 size_t vqgnn_mp_info_workspace_bytes(int64_t nnz, int C, int slab);
-int vqgnn_mp_info(const int32_t* rowptr, const int32_t* col, const float* val, int64_t e_begin, int64_t nnz,
+/* erow[e] = row of CSR entry e for the rows [r_begin, R) (the per-entry row ids vqgnn_mp_info streams). */
+int vqgnn_csr_expand_rows(const int32_t* rowptr, int64_t r_begin, int64_t R, int32_t* erow, void* stream);
+int vqgnn_mp_info(const int32_t* erow, const int32_t* col, const float* val, int64_t e_begin, int64_t nnz,
                   int64_t B, int64_t R, const float* x, int64_t ldx, const float* tfS, const float* tgS, int C,
                   int slab, float info_scale, float* info, void* ws, void* stream);
 

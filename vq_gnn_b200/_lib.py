@@ -58,6 +58,7 @@ _SIGNATURES = {
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "vqgnn_tail_materialize_slab": (C.c_int, [vp, i64, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "vqgnn_mp_info_workspace_bytes": (C.c_size_t, [i64, i32, i32]),
+    "vqgnn_csr_expand_rows": (C.c_int, [vp, i64, i64, vp, vp]),
     "vqgnn_mp_info": (C.c_int, [vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, vp, i32, i32, f32, vp, vp, vp]),
     "vqgnn_khop_workspace_bytes": (C.c_size_t, [i64, i64]),
     "vqgnn_khop_mark": (C.c_int, [vp, vp, vp, i64, i64, vp, vp, vp, vp, vp]),

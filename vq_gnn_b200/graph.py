@@ -148,6 +148,18 @@ class BatchPlan:
             n = self.extras['nnz_B'] = int(self.fwd_rowptr[self.B])
         return n
 
+    def entry_rows(self) -> Tensor:
+        """int32 [nnz]: row id of every forward-CSR entry of the rows >= B (entries of batch rows are not filled);
+        what vqgnn_mp_info streams instead of walking rowptr.  Built once per plan on the device."""
+        t = self.extras.get('erow')
+        if t is None:
+            from . import _lib
+            t = torch.empty(max(self.nnz, 1) + 4, dtype=torch.int32, device=self.device)
+            _lib.check(_lib.load().vqgnn_csr_expand_rows(_lib.ptr(self.fwd_rowptr), self.B, self.R, _lib.ptr(t),
+                                                         _lib.stream()))
+            self.extras['erow'] = t
+        return t
+
     @property
     def has_rval(self) -> bool:
         return self._has_rval if self._has_rval is not None else self.fwd_rval is not None
@@ -214,6 +226,9 @@ class BatchPlan:
             self.split_v1()
         else:
             self.chunk_rows('fwd')
+        if self.version == 'v2' and self.training and self.R > self.B and self.conv_type != 'GAT':
+            self.chunk_rows('fwdB')
+            self.entry_rows()
         return self
 
     def split_v1(self):

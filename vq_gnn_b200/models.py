@@ -122,7 +122,7 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(_mp_ws(dev, nB, MP_CHUNK, C)), st))
             iws = torch.empty(int(lib.vqgnn_mp_info_workspace_bytes(plan.nnz, C, slab)), dtype=torch.uint8, device=dev)
             _lib.check(lib.vqgnn_mp_info(
-                _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), nB, plan.nnz, B, plan.R,
+                _lib.ptr(plan.entry_rows()), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), nB, plan.nnz, B, plan.R,
                 _lib.ptr(x), x.stride(0), _lib.ptr(tfS), _lib.ptr(tgS), C, slab, float(wu), _lib.ptr(info),
                 _lib.ptr(iws), st))
         else:
