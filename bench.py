@@ -250,7 +250,15 @@ def algorithmic_work(kernel: str, plan, C: int, nb: int, M: int, B: int):
     index = 4 B; §8d's table).  Unknown kernels return (0, 'hbm')."""
     v1 = plan.version == 'v1'
     nnz = plan.nnz
+    if kernel == "vqgnn_mp_info":   # out-of-batch rows of the v2 forward: edge list + row pointers + codes + codebooks + x
+        nnz_o = nnz - plan.nnz_B
+        return nnz_o * 8 + (plan.T + 1) * 4 + plan.T * nb * 2 + 2 * M * C * 4 + B * C * 4, "hbm"
+    if kernel == "vqgnn_tail_materialize_slab":
+        return plan.T * nb * 2 + 2 * plan.T * C * 4 + 2 * M * C * 4, "hbm"
     if kernel in ("vqgnn_mp_fwd", "vqgnn_gat_fwd"):
+        if not v1 and 'erow' in plan.extras and kernel == "vqgnn_mp_fwd":   # batch rows only (split forward)
+            nB = plan.nnz_B
+            return nB * 8 + (B + 1) * 4 + 2 * B * C * 4 + nB * nb * 2 + M * C * 4, "hbm"
         if v1 and 'split' in plan.extras:      # in-batch block only (the tail goes through vqgnn_mp_fwd_tail)
             nin = int(plan.extras['split']['inb'][4])
             return nin * 8 + (B + 1) * 4 + 2 * B * C * 4, "hbm"
