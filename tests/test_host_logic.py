@@ -166,3 +166,25 @@ def test_link_head_matches_main_link():
     want = -torch.log(p(out[src], out[dst]) + 1e-15).mean() - torch.log(1 - p(out[src], out[dst_neg]) + 1e-15).mean()
     got = link.link_loss(pred, out, bA, dst_neg=dst_neg)
     assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+def test_rw_and_edge_samplers():
+    """rw / edge samplers (vq_gnn_v2/dataloader.py:71-75): walks follow edges, isolated nodes stay put, outputs unique."""
+    from vq_gnn_b200 import sampling
+    N = 300
+    g = H.make_graph(N, 900, "GCN", "v1", seed=8)          # v1 graphs store no diagonal
+    gen = torch.Generator().manual_seed(1)
+    seeds = torch.randperm(N, generator=gen)[:40]
+    w = sampling.random_walk(g, seeds, 4, generator=gen)
+    assert w.shape == (40, 5) and torch.equal(w[:, 0], seeds)
+    dense = torch.zeros(N, N, dtype=torch.bool)
+    dense[g.row, g.col] = True
+    deg = g.rowptr[1:] - g.rowptr[:-1]
+    for t in range(4):
+        a, b = w[:, t], w[:, t + 1]
+        ok = dense[a, b] | ((deg[a] == 0) & (a == b))
+        assert bool(ok.all())
+    nodes = sampling.rw_sampler(g, seeds, 4, generator=gen)
+    assert torch.equal(nodes, torch.unique(nodes)) and nodes.numel() <= 40 * 5
+    e = sampling.edge_sampler(g, seeds, generator=gen)
+    assert torch.equal(e, torch.unique(e)) and e.numel() <= 80 and bool(torch.isin(seeds, e).all())

@@ -4,7 +4,8 @@ Restates, in device-agnostic torch (runs on the GPU in bench.py, on CPU in tests
   * v2 `_k_hop_subgraph` (vq_gnn_v2/dataloader.py:98-148): subset = [B ; B'] with the batch nodes
     first, train keeps every edge inside B u B', eval keeps only rows in B, nodes relabelled;
   * v1 `__collate__` tail (vq_gnn_v1/utils/dataloader.py:64-86): `(deg_inv[B], A_BN, A_BB, A_NB_v, batch_idx)`;
-  * the `node` / `cluster` / `cont` samplers (vq_gnn_v2/dataloader.py:52-96).
+  * the `node` / `cluster` / `cont` / `rw` / `edge` samplers (vq_gnn_v2/dataloader.py:52-96); METIS itself is not
+    rebuilt: contiguous id blocks of a planted-partition graph stand in for its parts.
 The order of the B' nodes is unspecified in the reference (`unique(sorted=False)`); here it is ascending.
 """
 from __future__ import annotations
@@ -92,6 +93,35 @@ def cont_sampler(g: Graph, seeds: Tensor, walk_length: int, batch_size: int,
         cur = torch.unique(torch.where(deg > 0, nxt, cur))[:batch_size]
         out.append(cur)
     return out
+
+
+def random_walk(g: Graph, start: Tensor, walk_length: int,
+                generator: Optional[torch.Generator] = None) -> Tensor:
+    """`adj_t.random_walk(start, walk_length)` of torch_sparse as used by the loaders: uniform next-neighbour steps,
+    a node without neighbours stays where it is.  -> [len(start), walk_length + 1] node ids (column 0 = start)."""
+    dev = g.col.device
+    cur = start.to(dev)
+    out = [cur]
+    for _ in range(walk_length):
+        deg = g.rowptr[cur + 1] - g.rowptr[cur]
+        r = (torch.rand(cur.numel(), generator=generator, device=dev) * deg.clamp(min=1)).long()
+        nxt = g.col[(g.rowptr[cur] + r).clamp(max=max(g.nnz - 1, 0))]
+        cur = torch.where(deg > 0, nxt, cur)
+        out.append(cur)
+    return torch.stack(out, 1)
+
+
+def rw_sampler(g: Graph, seeds: Tensor, walk_length: int,
+               generator: Optional[torch.Generator] = None) -> Tensor:
+    """`rw` sampler (vq_gnn_v2/dataloader.py:74-75; v1 utils/dataloader.py:44-45): every node visited by one random
+    walk of `walk_length` steps from each seed (the loader passes batch_size // (walk_length + 1) seeds)."""
+    return torch.unique(random_walk(g, seeds, walk_length, generator).reshape(-1))
+
+
+def edge_sampler(g: Graph, seeds: Tensor, generator: Optional[torch.Generator] = None) -> Tensor:
+    """`edge` sampler (vq_gnn_v2/dataloader.py:71-72): the end points of one random edge per seed
+    (the loader passes batch_size // 2 seeds)."""
+    return torch.unique(random_walk(g, seeds, 1, generator).reshape(-1))
 
 
 def cluster_batch(N: int, num_parts: int, parts: Tensor) -> Tensor:
