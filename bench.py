@@ -500,6 +500,13 @@ def main():
         capacity = int(cap.item())
     model, head = build_model(c, dev, N, distributed, args.assign_impl, capacity)
     model.set_async_vq_updates(not args.sync_vq)
+    if distributed and not args.sync_vq:
+        # the side-stream VQ collectives get their OWN communicator: ProcessGroupNCCL funnels every collective of a
+        # group through one in-order NCCL stream, so sharing the default group would make the weight-gradient
+        # allreduce on the compute stream wait for all VQ updates issued before it
+        vq_group = torch.distributed.new_group()
+        for layer in model.convs:
+            layer.bank.process_group = vq_group
     use_graphs = not args.no_graphs
     params = list(model.parameters()) + (list(head.parameters()) if head is not None else [])
     opt = torch.optim.RMSprop(params, lr=c["lr"], alpha=0.99, capturable=use_graphs)
