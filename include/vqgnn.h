@@ -161,14 +161,17 @@ size_t vqgnn_mp_workspace_bytes(int64_t nnz, int chunk, int C);
 int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, const float* rval,
                  const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B, const float* x,
                  int64_t ldx, const int32_t* tail_node, const int16_t* codes, const float* O, int nb, int M,
-                 int D, int Wp, const float* tail_feat, int64_t ld_tail, float feat_scale, float info_scale,
-                 float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws, void* stream);
+                 int D, int Wp, const float* tail_feat, int64_t ld_tail, int tail_slab, float feat_scale,
+                 float info_scale, float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws,
+                 void* stream);
 
 /* Dense copies of the tail entries' codewords: tail_feat[t, 4k:4k+4] = O_k[code_k(node(t)), :4],
  * tail_grad[t, 4k:4k+4] = O_k[code_k(node(t)), 4:8] (either may be NULL; D == 4, Wp == 8).  In a v2 batch graph
  * a tail node is referenced by ~20 edges: gathering its codewords once and handing the rows to vqgnn_mp_fwd
  * (tail_feat) / vqgnn_mp_bwd (tail_grad) turns nb scattered sector reads per edge into one coalesced row read.
- * Both kernels fall back to per-edge codebook gathers when the pointer is NULL. */
+ * Both kernels fall back to per-edge codebook gathers when the pointer is NULL.  tail_slab > 0: the table handed to
+ * vqgnn_mp_fwd / vqgnn_mp_bwd is the SLAB-MAJOR one of vqgnn_tail_materialize_slab ([ceil(C/tail_slab)][T][tail_slab])
+ * and ld_tail carries T; tail_slab == 0: row-major [T, ld_tail]. */
 int vqgnn_tail_materialize(const int32_t* tail_node, int64_t T, const int16_t* codes, const float* O, int nb,
                            int M, int D, int Wp, float* tail_feat, float* tail_grad, int64_t ld_tail,
                            void* stream);
@@ -198,7 +201,7 @@ int vqgnn_mp_info(const int32_t* erow, const int32_t* col, const float* val, int
 int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval, const int32_t* chunk_row,
                  int chunk, int64_t nnz, int64_t B, const float* dy, int64_t lddy, const int32_t* tail_node,
                  const int16_t* codes, const float* O, int nb, int M, int D, int Wp, const float* tail_grad,
-                 int64_t ld_tail, float tail_scale, const float* gq, int64_t ldgq, float gq_scale,
+                 int64_t ld_tail, int tail_slab, float tail_scale, const float* gq, int64_t ldgq, float gq_scale,
                  const float* dinfo, float* dx, int64_t lddx, void* ws, void* stream);
 
 /* Out-of-batch ("tail") part of the forward with the codebooks of a branch group resident in shared

@@ -306,7 +306,7 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
                             const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
                             const float* x, int64_t ldx, const int32_t* tail_node, const int16_t* codes,
                             const float* O, int nb, int M, int D, int Wp, const float* tail_feat,
-                            int64_t ld_tail, float feat_scale, float info_scale,
+                            int64_t ld_tail, int tail_slab, float feat_scale, float info_scale,
                             float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws,
                             void* stream) {
   VQ_CHECK_ARG(rowptr && col && val && x && codes && O && y, "mp_fwd: null argument");
@@ -318,8 +318,9 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
   const int C = nb * D;
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
   if (tail_feat) {
-    VQ_CHECK_ARG(!rval && ld_tail % 4 == 0 && aligned16(tail_feat), "mp_fwd: dense tail rows need rval == NULL and 16 B alignment");
-    cb.tail_feat = tail_feat, cb.ld_tail = ld_tail;
+    VQ_CHECK_ARG(!rval && (tail_slab > 0 || ld_tail % 4 == 0) && tail_slab % 4 == 0 && aligned16(tail_feat),
+                 "mp_fwd: dense tail rows need rval == NULL and 16 B alignment");
+    cb.tail_feat = tail_feat, cb.ld_tail = ld_tail, cb.tail_slab = tail_slab;
   }
   MpWs w{nullptr, nullptr, nullptr, nullptr};
   if (ws) mp_ws_layout(ws, nnz, chunk, C, &w);
@@ -371,7 +372,8 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
 extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const float* bval,
                             const int32_t* chunk_row, int chunk, int64_t nnz, int64_t B, const float* dy,
                             int64_t lddy, const int32_t* tail_node, const int16_t* codes, const float* O, int nb,
-                            int M, int D, int Wp, const float* tail_grad, int64_t ld_tail, float tail_scale,
+                            int M, int D, int Wp, const float* tail_grad, int64_t ld_tail, int tail_slab,
+                            float tail_scale,
                             const float* gq, int64_t ldgq, float gq_scale, const float* dinfo, float* dx,
                             int64_t lddx, void* ws, void* stream) {
   VQ_CHECK_ARG(browptr && brow && bval && dy && codes && O && dx, "mp_bwd: null argument");
@@ -385,8 +387,9 @@ extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const f
   if (ws) mp_ws_layout(ws, nnz, chunk, C, &w);
   Codebook cb{tail_node, codes, O, nb, M, D, Wp};
   if (tail_grad) {
-    VQ_CHECK_ARG(ld_tail % 4 == 0 && aligned16(tail_grad), "mp_bwd: dense tail rows must be 16 B aligned");
-    cb.tail_grad = tail_grad, cb.ld_tail = ld_tail;
+    VQ_CHECK_ARG((tail_slab > 0 || ld_tail % 4 == 0) && tail_slab % 4 == 0 && aligned16(tail_grad),
+                 "mp_bwd: dense tail rows must be 16 B aligned");
+    cb.tail_grad = tail_grad, cb.ld_tail = ld_tail, cb.tail_slab = tail_slab;
   }
   const bool vec4 = (D == 4) && (Wp % 4 == 0) && (lddy % 4 == 0) && (lddx % 4 == 0) && aligned16(dy) &&
                     aligned16(dx) && aligned16(O) && (!gq || (ldgq % 4 == 0 && aligned16(gq)));

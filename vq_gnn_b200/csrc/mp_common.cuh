@@ -24,6 +24,14 @@ struct Codebook {
   const float* tail_feat = nullptr;  // [T, ld_tail] feature halves
   const float* tail_grad = nullptr;  // [T, ld_tail] gradient halves
   int64_t ld_tail = 0;
+  // tail_slab > 0: the two tables are SLAB-MAJOR, [ceil(C / tail_slab)][T][tail_slab] (vqgnn_tail_materialize_slab),
+  // and ld_tail holds T
+  int tail_slab = 0;
+  __device__ __forceinline__ const float* tail_row(const float* t, int te, int c0) const {
+    if (tail_slab == 0) return t + static_cast<int64_t>(te) * ld_tail + c0;
+    const int sl = c0 / tail_slab;
+    return t + (static_cast<int64_t>(sl) * ld_tail + te) * tail_slab + (c0 - sl * tail_slab);
+  }
 };
 
 template <int VEC>
@@ -226,7 +234,7 @@ __device__ __forceinline__ void gather_accumulate(const EntryGroup& g, int B, co
     float a[U][VEC];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (g.c[u] >= B) ld_vec<VEC>(tdense + static_cast<int64_t>(g.c[u] - B) * cb.ld_tail + c0, a[u]);
+      if (g.c[u] >= B) ld_vec<VEC>(cb.tail_row(tdense, g.c[u] - B, c0), a[u]);
       else if (g.c[u] >= 0) ld_vec<VEC>(dense + static_cast<int64_t>(g.c[u]) * ldd + c0, a[u]);
     }
 #pragma unroll

@@ -92,7 +92,7 @@ class VQConvFunction(torch.autograd.Function):
             _lib.check(lib.vqgnn_mp_fwd(
                 _lib.ptr(iptr), _lib.ptr(icol), _lib.ptr(ival), None, _lib.ptr(icr), plan.small_chunk, innz, B, B,
                 _lib.ptr(x), x.stride(0), None, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
-                bank.Wp, None, 0, 1.0, 1.0, _lib.ptr(y), y.stride(0), None, 0, None,
+                bank.Wp, None, 0, 0, 1.0, 1.0, _lib.ptr(y), y.stride(0), None, 0, None,
                 _lib.ptr(_mp_ws(dev, innz, plan.small_chunk, C)), st))
             ws = torch.empty(int(lib.vqgnn_mp_fwd_tail_workspace_bytes(tnnz, TAIL_CHUNK, B, C)), dtype=torch.uint8,
                              device=dev)
@@ -118,8 +118,9 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), None,
                 _lib.ptr(plan.chunk_rows('fwdB')), MP_CHUNK, nB, B, B, _lib.ptr(x), x.stride(0),
                 _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp,
-                None, 0, 1.0, float(wu), _lib.ptr(y), y.stride(0), None, 0, None,
+                _lib.ptr(tfS), plan.T, slab, 1.0, float(wu), _lib.ptr(y), y.stride(0), None, 0, None,
                 _lib.ptr(_mp_ws(dev, nB, MP_CHUNK, C)), st))
+            ctx.tail_grad, ctx.tail_slab = tgS, slab      # the backward reads the gradient codewords slab-major
             iws = torch.empty(int(lib.vqgnn_mp_info_workspace_bytes(plan.nnz, C, slab)), dtype=torch.uint8, device=dev)
             _lib.check(lib.vqgnn_mp_info(
                 _lib.ptr(plan.entry_rows()), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), nB, plan.nnz, B, plan.R,
@@ -142,13 +143,15 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
                 _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
                 _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
-                _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C,
+                _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C, 0,
                 float(wu) if v1 else 1.0, float(wu),
                 _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
                 _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
         ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook = layer, plan, float(wu), fire_hook
         if not hasattr(ctx, 'tail_grad'):
             ctx.tail_grad = None
+        if not hasattr(ctx, 'tail_slab'):
+            ctx.tail_slab = 0
         ctx.save_for_backward(x, gq)
         return y, info
 
@@ -170,7 +173,8 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
                 _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
                 dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
-                bank.M, bank.D, bank.Wp, _lib.ptr(ctx.tail_grad), C, 0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
+                bank.M, bank.D, bank.Wp, _lib.ptr(ctx.tail_grad), plan.T if ctx.tail_slab else C, ctx.tail_slab,
+                0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
                 wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0),
                 _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
         if ctx.fire_hook:
@@ -203,7 +207,7 @@ def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Ten
     if att_l is None:
         _lib.check(lib.vqgnn_mp_fwd(
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), None, _lib.ptr(chunks), MP_CHUNK, nnz,
-            n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, None, 0, 1.0, 1.0,
+            n, n, _lib.ptr(xc), xc.stride(0), None, _lib.ptr(codes), _lib.ptr(O), C // D, 1, D, 8, None, 0, 0, 1.0, 1.0,
             _lib.ptr(y), y.stride(0), None, 0, None, _lib.ptr(_mp_ws(x.device, nnz, MP_CHUNK, C)), st))
         return y
     # GAT: the fused kernels carry an implicit ones column (coefficient att[C]); a zero coefficient removes it from
