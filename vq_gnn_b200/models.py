@@ -342,9 +342,12 @@ class LowRankGNNLayer(nn.Module):
         # True = when tail nodes are referenced >= 4x on average (measured per layer: arxiv 1.61 -> 1.50 ms, collab
         # 1.59 -> 1.49, products forward 2.09 -> 1.17 + 0.18 ms), 'force' = always, False = never
         self.materialize_tail = True
-        # v2 training: batch rows and out-of-batch rows (info_backward only) through separate kernels when the latter
-        # hold >= INFO_SPLIT_MIN_ENTRIES entries (csrc/mp_info.cu); 'force' = always, False = never
-        self.split_info = True
+        # v2 training: batch rows and out-of-batch rows (info_backward only) through separate kernels (csrc/mp_info.cu:
+        # slab-major tables, L2-resident slices).  True = when the latter hold >= INFO_SPLIT_MIN_ENTRIES entries,
+        # 'force' = always, False (default) = never: measured at the products shape both forms run at the same
+        # ~5.5 TB/s of on-chip gather traffic (1.50 vs 1.60 ms per layer) and the split pays a second small launch for
+        # the batch rows (step 9.2 vs 8.5 ms), so the one-kernel forward stays the default
+        self.split_info = False
         self._restack()
 
     # ---- stacked storage <-> per-branch reference buffers -------------------------------------
