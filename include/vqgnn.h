@@ -119,7 +119,8 @@ int vqgnn_vq_segsum(const float* x, int64_t ldx, const float* g, int64_t ldg, co
                     const float* shift, const int16_t* idx, int64_t B, int nbc, int M, int D, int Dg, int Wp,
                     float* stats, void* ws, size_t ws_bytes, void* stream);
 
-/* EMA + Laplace smoothing + codeword recovery (vq.py:177-200 / 242-275), one CTA per branch:
+/* EMA + Laplace smoothing + codeword recovery (vq.py:177-200 / 242-275); sizes by one CTA per branch, then
+ * (branch, 256-codeword tile) CTAs for the sums / codewords:
  *   size <- decay*size + (1-decay)*count; if warm_up: size <- (size+1e-5)/(sum(size)+M*1e-5)*sum(size);
  *   status |= BAD_INIT if any size == 0 and, as the reference raises before touching them (vq.py:188,253), Wm / E /
  *   O of that branch are then left unchanged; otherwise Wm <- decay*Wm + (1-decay)*sum_z; E <- Wm/size;

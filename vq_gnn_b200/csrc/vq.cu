@@ -227,17 +227,17 @@ __global__ void __launch_bounds__(kAssignThreads)
 }
 
 // ------------------------------------------------------------------------------------------------
-// (4) EMA + Laplace smoothing + codeword recovery: one CTA per branch
+// (4) EMA + Laplace smoothing + codeword recovery, two launches:
+//   vq_finalize_size_kernel : one CTA per branch -- cluster sizes (needs the branch total for the Laplace smoothing)
+//   vq_finalize_code_kernel : (branch, tile of codewords) CTAs -- EMA sums, codewords, recovery; a branch whose sizes
+//                             contain a zero is left untouched ('Bad Init!', vq.py:188-189 / 253-254)
 // ------------------------------------------------------------------------------------------------
 constexpr int kFinThreads = 512;
+constexpr int kFinTile = 256;   // codewords per CTA of the second launch
 
 __global__ void __launch_bounds__(kFinThreads)
-    vq_finalize_kernel(const float* __restrict__ stats, int M, int D, int Dg, int Wp, int joint, float decay,
-                       float omd, int warm_up, float eps, float gs0, float gs1,
-                       const float* __restrict__ run_mean_f, const float* __restrict__ run_var_f,
-                       const float* __restrict__ run_mean_g, const float* __restrict__ run_var_g,
-                       float* __restrict__ ema_size, float* __restrict__ ema_w, float* __restrict__ E,
-                       float* __restrict__ O, int32_t* __restrict__ status) {
+    vq_finalize_size_kernel(const float* __restrict__ stats, int M, int Wp, float decay, float omd, int warm_up,
+                            float* __restrict__ ema_size, int32_t* __restrict__ status) {
   const int k = blockIdx.x, tid = threadIdx.x;
   const int Ws = Wp + 4;
   const float* st = stats + static_cast<int64_t>(k) * M * Ws;
@@ -275,20 +275,31 @@ __global__ void __launch_bounds__(kFinThreads)
   }
   if (bad) atomicOr(&bad_sh, 1);
   __syncthreads();
-  if (bad_sh) {
-    // vq.py:188-189 / 253-254 raise 'Bad Init!' BEFORE _ema_w / _embedding / _embedding_output are touched (the
-    // cluster sizes are already updated at that point): leave them as they are instead of dividing by zero
-    if (tid == 0) atomicOr(status, VQGNN_STATUS_BAD_INIT);
-    return;
-  }
+  if (tid == 0 && bad_sh) atomicOr(status, VQGNN_STATUS_BAD_INIT);
+}
 
-  // ema_w, E, O
+__global__ void __launch_bounds__(256)
+    vq_finalize_code_kernel(const float* __restrict__ stats, int M, int D, int Dg, int Wp, int joint, float decay,
+                            float omd, float eps, float gs0, float gs1, const float* __restrict__ run_mean_f,
+                            const float* __restrict__ run_var_f, const float* __restrict__ run_mean_g,
+                            const float* __restrict__ run_var_g, const float* __restrict__ ema_size,
+                            float* __restrict__ ema_w, float* __restrict__ E, float* __restrict__ O) {
+  const int k = blockIdx.y, tid = threadIdx.x;
+  const int Ws = Wp + 4;
+  const float* st = stats + static_cast<int64_t>(k) * M * Ws;
+  const float* size = ema_size + static_cast<int64_t>(k) * M;
+  // the reference raises before it touches _ema_w / _embedding / _embedding_output: skip the whole branch
+  int bad = 0;
+  for (int m = tid; m < M; m += 256) bad |= (size[m] == 0.f);
+  if (__syncthreads_or(bad)) return;
+
   const int W = D + Dg;
   const int wlim = joint ? W : D;
   const float div0 = static_cast<float>(static_cast<double>(gs0) + static_cast<double>(eps));
   const float div1 = static_cast<float>(static_cast<double>(gs1) + static_cast<double>(eps));
-  for (int i = tid; i < M * wlim; i += kFinThreads) {
-    const int m = i / wlim, w = i - m * wlim;
+  const int m0 = blockIdx.x * kFinTile, m1 = min(m0 + kFinTile, M);
+  for (int i = tid; i < (m1 - m0) * wlim; i += 256) {
+    const int m = m0 + i / wlim, w = i - (i / wlim) * wlim;
     const int64_t off = (static_cast<int64_t>(k) * M + m) * Wp + w;
     const float wm = ema_w[off] * decay + omd * st[static_cast<int64_t>(m) * Ws + w];
     ema_w[off] = wm;
@@ -422,9 +433,13 @@ extern "C" int vqgnn_vq_finalize(const float* stats, int nb, int M, int D, int D
   // python: `size * decay + (1 - decay) * counts` with decay a double scalar cast to fp32 per operand
   const float decay_f = static_cast<float>(decay);
   const float omd = static_cast<float>(1.0 - decay);
-  vq_finalize_kernel<<<nb, kFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      stats, M, D, joint ? Dg : 0, Wp, joint, decay_f, omd, warm_up, eps, grad_scale0, grad_scale1, run_mean_f,
-      run_var_f, run_mean_g, run_var_g, ema_size, ema_w, E, O, status);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  vq_finalize_size_kernel<<<nb, kFinThreads, 0, s>>>(stats, M, Wp, decay_f, omd, warm_up, ema_size, status);
+  VQ_LAUNCH_CHECK();
+  dim3 grid(ceil_div(M, kFinTile), nb);
+  vq_finalize_code_kernel<<<grid, 256, 0, s>>>(stats, M, D, joint ? Dg : 0, Wp, joint, decay_f, omd, eps, grad_scale0,
+                                               grad_scale1, run_mean_f, run_var_f, run_mean_g, run_var_g, ema_size,
+                                               ema_w, E, O);
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }
