@@ -256,7 +256,7 @@ def algorithmic_work(kernel: str, plan, C: int, nb: int, M: int, B: int):
     if kernel == "vqgnn_tail_materialize_slab":
         return plan.T * nb * 2 + 2 * plan.T * C * 4 + 2 * M * C * 4, "hbm"
     if kernel in ("vqgnn_mp_fwd", "vqgnn_gat_fwd"):
-        if not v1 and 'erow' in plan.extras and kernel == "vqgnn_mp_fwd":   # batch rows only (split forward)
+        if not v1 and plan.extras.get('split_fwd') and kernel == "vqgnn_mp_fwd":   # batch rows only (split forward)
             nB = plan.nnz_B
             return nB * 8 + (B + 1) * 4 + 2 * B * C * 4 + nB * nb * 2 + M * C * 4, "hbm"
         if v1 and 'split' in plan.extras:      # in-batch block only (the tail goes through vqgnn_mp_fwd_tail)

@@ -226,9 +226,6 @@ class BatchPlan:
             self.split_v1()
         else:
             self.chunk_rows('fwd')
-        if self.version == 'v2' and self.training and self.R > self.B and self.conv_type != 'GAT':
-            self.chunk_rows('fwdB')
-            self.entry_rows()
         return self
 
     def split_v1(self):

@@ -107,6 +107,7 @@ class VQConvFunction(torch.autograd.Function):
             # Batch rows through the generic kernel (y), the rest through the slab-ordered SDDMM-shaped kernel whose
             # gathers stay L2-resident (csrc/mp_info.cu).
             slab = INFO_SLAB
+            plan.extras['split_fwd'] = True
             nslab = (C + slab - 1) // slab
             tfS = torch.empty(nslab, plan.T, slab, device=dev)
             tgS = torch.empty(nslab, plan.T, slab, device=dev)
