@@ -15,6 +15,8 @@
 //
 // Reference maths: vq_gnn_v2/models.py:161-198, vq_gnn_v2/convs.py:65-101,
 // vq_gnn_v1/models.py:170-223 + vq_gnn_v1/utils/dataloader.py:144-192.
+#include <cstdlib>
+
 #include "mp_common.cuh"
 
 namespace vqgnn {
@@ -101,6 +103,127 @@ __global__ void __launch_bounds__(kMpWarps * 32)
       walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body_dense, flush);
     else
       walk_rows<HAS_GQ>(t.eb, t.ee, t.row0, R, rowptr, col, val, rval, B, cb.tail_node, lane, pol, body, flush);
+  }
+  if (info) info_reduce_ordered(static_cast<double>(fpart), ws_part, ws_count, info_scale, info);
+}
+
+// Dense-tail forward with a deep asynchronous gather pipeline (the v2 forward of large batch graphs, where the
+// kernel is bound by the LATENCY of its 512 B row gathers: ncu showed 34 % occupancy, long-scoreboard stalls and
+// < 30 % of the L2 / DRAM throughput).  Same work partition and the same in-order accumulation as mp_fwd_kernel,
+// but every entry's row -- x[c] for a batch column, tail_feat[c - B] otherwise -- is copied global -> shared with
+// cp.async (16 B per lane, no registers held) kAsyncDepth entries ahead of its use, so each warp keeps kAsyncDepth
+// rows in flight instead of kMpUnroll.
+constexpr int kAsyncDepth = 12;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(kMpWarps * 32)
+    mp_fwd_async_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                        const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks,
+                        int chunk, int nnz, int64_t R, int B, const float* __restrict__ x, int64_t ldx, Codebook cb,
+                        int C, int nslab, float info_scale, float* __restrict__ y, int64_t ldy,
+                        float* __restrict__ info, double* ws_part, unsigned int* ws_count, float* __restrict__ py) {
+  extern __shared__ __align__(16) unsigned char async_smem[];   // [kMpWarps][kAsyncDepth][32 lanes] float4
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const MpTask t = mp_task<4>(chunk_row, n_chunks, chunk, nnz, nslab, C, cb.D);
+  float fpart = 0.f;
+  if (t.valid) {
+    const int c0 = t.c0;
+    const int64_t ch = t.eb / chunk;
+    float4* ring = reinterpret_cast<float4*>(async_smem) + (warp * kAsyncDepth) * 32 + lane;
+    const uint32_t ring_s = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = t.row0, rbase = r;
+    int rp_l = __ldg(rowptr + min(static_cast<int64_t>(rbase) + lane, R));
+    int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
+
+    auto flush = [&](bool whole) {
+      if (t.active) {
+        if (r < B) {
+          const int kind = piece_kind(whole, rs, re, t.eb, chunk);
+          float* yp = y + static_cast<int64_t>(r) * ldy + c0;
+          if (kind == kPieceWhole) st_vec<4>(yp, acc);
+          else if (kind == kPieceRed) red_vec<4>(yp, acc);
+          else st_vec<4>(py + (ch * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + c0, acc);
+        } else if (info) {  // v2: <Y[r], Gq[r]> with Gq the node's own gradient codeword (models.py:198)
+          const int node = cb.tail_node ? __ldg(cb.tail_node + (r - B)) : (r - B);
+          const int code = __ldg(cb.codes + static_cast<int64_t>(node) * cb.nb + t.k);
+          float gv[4];
+          ld_vec<4>(cb.O + (static_cast<int64_t>(t.k) * cb.M + code) * cb.Wp + cb.D + t.off, gv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) fpart = fmaf(acc[i], gv[i], fpart);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = 0.f;
+    };
+
+    // entry e of the chunk lives in lane (e - t.eb) % 32 of batch (e - t.eb) / 32; two batches are held in registers
+    int c_cur = -1, c_nxt = -1;
+    float v_cur = 0.f, v_nxt = 0.f;
+    auto load_batch = [&](int bb, int& c_l, float& v_l) {
+      const int e = bb + lane;
+      c_l = -1, v_l = 0.f;
+      if (e < t.ee) c_l = __ldg(col + e), v_l = __ldg(val + e);
+    };
+    load_batch(t.eb, c_cur, v_cur);
+    load_batch(t.eb + 32, c_nxt, v_nxt);
+    // issue the copy of entry `e` (its column id is in c_cur / c_nxt of lane (e - eb) % 32) into ring slot e % depth
+    auto issue = [&](int e, int bb_cur) {
+      if (e < t.ee) {
+        const int src_lane = (e - t.eb) & 31;
+        const int c = __shfl_sync(0xffffffffu, e < bb_cur + 32 ? c_cur : c_nxt, src_lane);
+        if (t.active) {
+          const float* p = c >= B ? cb.tail_feat + static_cast<int64_t>(c - B) * cb.ld_tail + c0
+                                  : x + static_cast<int64_t>(c) * ldx + c0;
+          cp_async16(ring_s + ((e - t.eb) % kAsyncDepth) * 32 * 16, p);
+        }
+      }
+      cp_async_commit();   // one group per entry, also past the end: the wait below counts groups
+    };
+    for (int e = t.eb; e < t.eb + kAsyncDepth; ++e) issue(e, t.eb);
+
+    bool pending = false;
+    for (int bb = t.eb; bb < t.ee; bb += 32) {
+      const int bend = min(bb + 32, t.ee);
+      for (int e = bb; e < bend; ++e) {
+        const float v = __shfl_sync(0xffffffffu, v_cur, e - bb);
+        cp_async_wait<kAsyncDepth - 1>();
+        if (t.active) {
+          const float4 a = ring[((e - t.eb) % kAsyncDepth) * 32];
+          acc[0] = fmaf(v, a.x, acc[0]), acc[1] = fmaf(v, a.y, acc[1]);
+          acc[2] = fmaf(v, a.z, acc[2]), acc[3] = fmaf(v, a.w, acc[3]);
+        }
+        issue(e + kAsyncDepth, bb);
+        pending = true;
+        if (e + 1 == re) {   // row r complete
+          flush(rs >= t.eb);
+          pending = false;
+          if (e + 1 < t.ee) {
+            do {  // next non-empty row
+              ++r;
+              if (r - rbase >= 31) {
+                rbase = r;
+                rp_l = __ldg(rowptr + min(static_cast<int64_t>(rbase) + lane, R));
+              }
+              rs = __shfl_sync(0xffffffffu, rp_l, r - rbase);
+              re = __shfl_sync(0xffffffffu, rp_l, r - rbase + 1);
+            } while (re <= e + 1);
+          }
+        }
+      }
+      c_cur = c_nxt, v_cur = v_nxt;
+      load_batch(bb + 64, c_nxt, v_nxt);
+    }
+    if (pending) flush(false);
+    cp_async_wait<0>();
   }
   if (info) info_reduce_ordered(static_cast<double>(fpart), ws_part, ws_count, info_scale, info);
 }
@@ -341,6 +464,25 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
   const int nslab = ceil_div(C, 32 * vec);
   const int64_t tasks = static_cast<int64_t>(n_chunks) * nslab;
   const int grid = ceil_div(tasks, kMpWarps);
+  static const bool use_async = []() {
+    const char* e = getenv("VQGNN_MPFWD_ASYNC");
+    return !(e && e[0] == '0');
+  }();
+  if (use_async && vec4 && tail_feat && tail_slab == 0 && !rval && feat_scale == 1.0f && C >= 64) {
+    // large v2 batch graphs with materialised tail rows: deep cp.async gather pipeline
+    const size_t smem = static_cast<size_t>(kMpWarps) * kAsyncDepth * 32 * 16;
+    VQ_CUDA(cudaFuncSetAttribute(mp_fwd_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mp_fwd_async_kernel<<<grid, kMpWarps * 32, smem, s>>>(rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, R, (int)B,
+                                                          x, ldx, cb, C, nslab, info_scale, y, ldy, info, w.part,
+                                                          w.count, w.p0);
+    VQ_LAUNCH_CHECK();
+    if (n_chunks > 2) {
+      mp_fixup_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, y, ldy,
+                                                        nullptr, gq, ldgq);
+      VQ_LAUNCH_CHECK();
+    }
+    return VQGNN_OK;
+  }
 #define VQ_MP_FWD(VEC, GQ, WIDE)                                                                              \
   mp_fwd_kernel<VEC, GQ, WIDE><<<grid, kMpWarps * 32, 0, s>>>(rowptr, col, val, rval, chunk_row, n_chunks,    \
                                                               chunk, (int)nnz, R, (int)B, x, ldx, cb, C, nslab, \
