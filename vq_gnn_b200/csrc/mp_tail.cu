@@ -32,14 +32,16 @@ __device__ __forceinline__ void red_v4(float* p, const float (&v)[4]) {
                : "memory");
 }
 
-// Lane mapping: G = 8 branches per group; a warp advances 4 entries per sub-step, lane = slot * 8 + g gathers branch
-// g's codeword HALF (4 floats, one LDS.128) of the entry in `slot`.  The two halves are separate passes ("half
-// groups"): features -> y with val * feat_scale, gradients -> gq with rval.
+// Lane mapping: G = 8 branches per group; a warp advances 8 entries per sub-step, lane = slot * 4 + q gathers the
+// codeword HALVES (4 floats, one LDS.128 each) of branches 2q and 2q+1 of the entry in `slot` -- odd slots in the
+// opposite order, so the eight lanes of every LDS.128 phase (two entries x four lanes) still cover the eight bank
+// groups.  The two halves are separate passes ("half groups"): features -> y with val * feat_scale, gradients -> gq
+// with rval.
 // Shared-memory layout of a half group: chunk (code, g) at byte code * 128 + g * 16, i.e. the eight lanes of an
 // LDS.128 phase (one entry's eight branches) always hit eight DIFFERENT 16 B bank groups whatever the codes are:
 // the random gathers are bank-conflict free by construction (M * 128 B <= 192 KB: M <= 1536).
 constexpr int kTailG = 8;
-constexpr int kTailEPS = 4;     // entries per sub-step
+constexpr int kTailEPS = 8;     // entries per sub-step
 constexpr int kTailBatch = 32;  // entries staged per batch (one per lane)
 
 __global__ void __launch_bounds__(kTailThreads, 1)
@@ -57,7 +59,8 @@ __global__ void __launch_bounds__(kTailThreads, 1)
   unsigned char* cb_ptr = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(cb_smem) + 127) & ~uintptr_t(127));
   const uint32_t cb_base = static_cast<uint32_t>(__cvta_generic_to_shared(cb_ptr));
   const uint32_t st_base = static_cast<uint32_t>(__cvta_generic_to_shared(&stage[warp][0]));
-  const int slot = lane >> 3, g = lane & 7;
+  const int slot = lane >> 2, q = lane & 3;
+  const int gA = 2 * q + (slot & 1), gB = 2 * q + 1 - (slot & 1);   // branch gathered first / second
   __shared__ int next_chunk;  // warps of the CTA draw the item's chunks dynamically
   if (d_nnz) {  // entry count only known on the device (vqgnn_plan_v1_build): the host sized the grid by an upper bound
     nnz = __ldg(d_nnz);
@@ -95,10 +98,11 @@ __global__ void __launch_bounds__(kTailThreads, 1)
     __syncthreads();  // every warp is done with the previous item (and its chunk counter)
     if (threadIdx.x == 0) next_chunk = c_begin;
     __syncthreads();
-    const bool g_on = g < gcount;
-    const uint32_t my_cb = cb_base + g * 16;
-    const uint32_t my_st = st_base + slot * 16 + g * 2;
-    const int colbase = (kbase + g) * 4;
+    const bool onA = gA < gcount, onB = gB < gcount;
+    const uint32_t cbA = cb_base + gA * 16, cbB = cb_base + gB * 16;
+    const uint32_t my_st = st_base + slot * 16 + q * 4;    // the u32 holding the codes of branches 2q (low) / 2q+1
+    const int shA = (slot & 1) * 16, shB = 16 - shA;        // which half of that word is branch gA / gB
+    const int colbase = (kbase + 2 * q) * 4;                 // 8 contiguous columns: branches 2q, 2q+1
 
     while (true) {
       int ch = 0;
@@ -106,31 +110,44 @@ __global__ void __launch_bounds__(kTailThreads, 1)
       ch = __shfl_sync(0xffffffffu, ch, 0);
       if (ch >= c_end) break;
       const int eb = ch * chunk, ee = min(eb + chunk, nnz);
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
       // rows: lane i holds rowptr[rbase + i]
       int r = __ldg(chunk_row + ch);
       int rbase = r;
       int rp_l = __ldg(rowptr + min(rbase + lane, B));
       int rs = __shfl_sync(0xffffffffu, rp_l, 0), re = __shfl_sync(0xffffffffu, rp_l, 1);
 
-      // the current row segment is complete: sum the 4 slots of every column into the slot-0 lanes and emit
+      // the current row segment is complete: sum the 8 slots of every column into the slot-0 lanes and emit
       auto flush = [&](bool whole) {
-        float t[4];
+        float t[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          t[i] = acc[i];
-#pragma unroll
-          for (int sI = 1; sI < EPS; ++sI) t[i] += __shfl_sync(0xffffffffu, acc[i], sI * G + g);
-          acc[i] = 0.f;
+        for (int i = 0; i < 4; ++i) {   // t[0..4) = branch 2q, t[4..8) = branch 2q+1 (odd slots hold them swapped)
+          t[i] = (slot & 1) ? accB[i] : accA[i];
+          t[4 + i] = (slot & 1) ? accA[i] : accB[i];
+          accA[i] = 0.f, accB[i] = 0.f;
         }
-        if (slot == 0 && g_on) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          t[i] += __shfl_xor_sync(0xffffffffu, t[i], 4);
+          t[i] += __shfl_xor_sync(0xffffffffu, t[i], 8);
+          t[i] += __shfl_xor_sync(0xffffffffu, t[i], 16);
+        }
+        if (slot == 0 && 2 * q < gcount) {
           const int kind = piece_kind(whole, rs, re, eb, chunk);
+          const bool two = 2 * q + 1 < gcount;
           float* dst = out + static_cast<int64_t>(r) * ldo + colbase;
-          if (kind == kPieceWhole) *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
-          else if (kind == kPieceRed) red_v4(dst, t);
-          else
-            *reinterpret_cast<float4*>(pout + (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C +
-                                       colbase) = make_float4(t[0], t[1], t[2], t[3]);
+          float* pdst = pout + (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + colbase;
+          const float lo[4] = {t[0], t[1], t[2], t[3]}, hi[4] = {t[4], t[5], t[6], t[7]};
+          if (kind == kPieceWhole) {
+            *reinterpret_cast<float4*>(dst) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            if (two) *reinterpret_cast<float4*>(dst + 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          } else if (kind == kPieceRed) {
+            red_v4(dst, lo);
+            if (two) red_v4(dst + 4, hi);
+          } else {
+            *reinterpret_cast<float4*>(pdst) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            if (two) *reinterpret_cast<float4*>(pdst + 4) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          }
         }
       };
       auto next_row = [&](int upto) {   // advance to the row that holds entry `upto`
@@ -180,20 +197,28 @@ __global__ void __launch_bounds__(kTailThreads, 1)
         const int bend = min(bb + BATCH, ee);
         if (bend - bb == BATCH && bend <= re) {
           // fast path (the usual case: rows are hundreds of entries long): the whole batch belongs to the current row,
-          // no row bookkeeping inside -- per sub-step 1 SHFL + 1 LDS.U16 + 1 conflict-free LDS.128 + 4 FFMA per lane
+          // no row bookkeeping inside -- per sub-step 1 SHFL + 1 LDS.32 + 2 conflict-free LDS.128 + 8 FFMA per lane
           uint32_t code[BATCH / EPS];
 #pragma unroll
           for (int j = 0; j < BATCH / EPS; ++j)
-            asm("ld.shared.u16 %0, [%1];" : "=r"(code[j]) : "r"(my_st + j * EPS * 16));
+            asm("ld.shared.u32 %0, [%1];" : "=r"(code[j]) : "r"(my_st + j * EPS * 16));
 #pragma unroll
           for (int j = 0; j < BATCH / EPS; ++j) {
             const float vf = __shfl_sync(0xffffffffu, v_l, j * EPS + slot);
-            if (g_on) {
+            const uint32_t ca = (code[j] >> shA) & 0xffffu, cb2 = (code[j] >> shB) & 0xffffu;
+            if (onA) {
               float4 f;
               asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                   : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                  : "r"(my_cb + code[j] * 128));
-              acc[0] = fmaf(vf, f.x, acc[0]), acc[1] = fmaf(vf, f.y, acc[1]), acc[2] = fmaf(vf, f.z, acc[2]), acc[3] = fmaf(vf, f.w, acc[3]);
+                  : "r"(cbA + ca * 128));
+              accA[0] = fmaf(vf, f.x, accA[0]), accA[1] = fmaf(vf, f.y, accA[1]), accA[2] = fmaf(vf, f.z, accA[2]), accA[3] = fmaf(vf, f.w, accA[3]);
+            }
+            if (onB) {
+              float4 f;
+              asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                  : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                  : "r"(cbB + cb2 * 128));
+              accB[0] = fmaf(vf, f.x, accB[0]), accB[1] = fmaf(vf, f.y, accB[1]), accB[2] = fmaf(vf, f.z, accB[2]), accB[3] = fmaf(vf, f.w, accB[3]);
             }
           }
           pending = true;
@@ -208,14 +233,20 @@ __global__ void __launch_bounds__(kTailThreads, 1)
           const int src = q0 - bb + slot;
           const int e = q0 + slot;
           const float vf0 = __shfl_sync(0xffffffffu, v_l, src);
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool live = g_on && e < bend;
+          float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
+          const bool live = e < bend;
           if (live) {
             uint32_t code;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(code) : "r"(st_base + src * 16 + g * 2));
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
-                         : "r"(my_cb + code * 128));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(code) : "r"(st_base + src * 16 + q * 4));
+            const uint32_t ca = (code >> shA) & 0xffffu, cb2 = (code >> shB) & 0xffffu;
+            if (onA)
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(fa.x), "=f"(fa.y), "=f"(fa.z), "=f"(fa.w)
+                           : "r"(cbA + ca * 128));
+            if (onB)
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(fb.x), "=f"(fb.y), "=f"(fb.z), "=f"(fb.w)
+                           : "r"(cbB + cb2 * 128));
           }
           const int qend = min(q0 + EPS, bend);
           int j0 = q0;
@@ -223,7 +254,8 @@ __global__ void __launch_bounds__(kTailThreads, 1)
             const int pend = min(re, qend);
             const bool on = live && e >= j0 && e < pend;
             const float vf = on ? vf0 : 0.f;
-            acc[0] = fmaf(vf, f.x, acc[0]), acc[1] = fmaf(vf, f.y, acc[1]), acc[2] = fmaf(vf, f.z, acc[2]), acc[3] = fmaf(vf, f.w, acc[3]);
+            accA[0] = fmaf(vf, fa.x, accA[0]), accA[1] = fmaf(vf, fa.y, accA[1]), accA[2] = fmaf(vf, fa.z, accA[2]), accA[3] = fmaf(vf, fa.w, accA[3]);
+            accB[0] = fmaf(vf, fb.x, accB[0]), accB[1] = fmaf(vf, fb.y, accB[1]), accB[2] = fmaf(vf, fb.z, accB[2]), accB[3] = fmaf(vf, fb.w, accB[3]);
             pending = true;
             j0 = pend;
             if (pend == re) {  // row r complete
