@@ -432,7 +432,7 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
                             int64_t ld_tail, int tail_slab, float feat_scale, float info_scale,
                             float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws,
                             void* stream) {
-  VQ_CHECK_ARG(rowptr && col && val && x && codes && O && y, "mp_fwd: null argument");
+  VQ_CHECK_ARG(rowptr && x && codes && O && y && (nnz == 0 || (col && val)), "mp_fwd: null argument");
   VQ_CHECK_ARG(R >= B && B > 0 && nb > 0 && D > 0 && Wp >= 2 * D, "mp_fwd: bad sizes");
   VQ_CHECK_ARG(ws || nnz == 0, "mp_fwd: needs a workspace of vqgnn_mp_workspace_bytes(nnz, chunk, nb*D) bytes");
   VQ_CHECK_ARG(B < (1ll << 31) && R < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "mp_fwd: sizes must fit int32");
@@ -518,7 +518,7 @@ extern "C" int vqgnn_mp_bwd(const int32_t* browptr, const int32_t* brow, const f
                             float tail_scale,
                             const float* gq, int64_t ldgq, float gq_scale, const float* dinfo, float* dx,
                             int64_t lddx, void* ws, void* stream) {
-  VQ_CHECK_ARG(browptr && brow && bval && dy && codes && O && dx, "mp_bwd: null argument");
+  VQ_CHECK_ARG(browptr && dy && codes && O && dx && (nnz == 0 || (brow && bval)), "mp_bwd: null argument");
   VQ_CHECK_ARG(B > 0 && B < (1ll << 31) && nb > 0 && D > 0 && Wp >= 2 * D, "mp_bwd: bad sizes");
   VQ_CHECK_ARG(nnz >= 0 && nnz < (1ll << 31), "mp_bwd: nnz must fit int32");
   VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && (nnz == 0 || chunk_row), "mp_bwd: needs chunk_row (vqgnn_mp_chunk_rows)");
