@@ -407,3 +407,23 @@ def test_v2_split_info_kernel(conv, C, slab, monkeypatch):
     c_outs = _run_cuda(layer, batch_A, x, 3, dev, wu=0.8)
     _compare(c_outs, _run_oracle(o, batch_A, x, 3, wu=0.8, cuda_outs=c_outs), layer, o)
     assert abs(float(c_outs[-1][1])) > 0
+
+
+def test_v1_tail_kernel_without_in_batch_block():
+    """v1 SAGE batch without A_BB (recovery_flag=False: every neighbour goes through its codeword, no self loops):
+    the in-batch CSR is EMPTY and the shared-memory tail kernel carries the whole forward (the reference's init()
+    feeds such batches, main_node.py:17-37)."""
+    dev = torch.device("cuda:0")
+    N, B, M, C = 500, 100, 16, 8
+    g = H.make_graph(N, 9000, "SAGE", "v1", seed=14)
+    batch_A = H.make_batch(g, B, "v1", seed=14, train=True, recovery=False)
+    assert batch_A[2] is None
+    torch.manual_seed(19)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, 6, M, 4, N, "SAGE"), version="v1")
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, 6, M, 4, N, "SAGE", "v1", warm_up_flag=True).load_state_dict(sd)
+    layer = layer.to(dev)
+    layer.use_tail_kernel = 'force'
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    c_outs = _run_cuda(layer, batch_A, x, 3, dev)
+    _compare(c_outs, _run_oracle(o, batch_A, x, 3, cuda_outs=c_outs), layer, o)
