@@ -174,7 +174,10 @@ class Workload:
                 parts = torch.randperm(cfg["parts"], generator=gcpu)[:cfg["batch_parts"]]
                 node_lists.append(sampling.cluster_batch(N, cfg["parts"], parts).to(dev))
         self.node_lists = [n.contiguous() for n in node_lists]
-        self.batches = [self.make_batch(n) for n in self.node_lists]
+        # (features, None, labels) per batch: the batch GRAPHS are built by the product itself
+        # (LowRankGNN.prepare_from_graph, csrc/khop.cu); make_batch() restates one in the reference's host format
+        # for the CPU arm only
+        self.batches = [(self.X[n], None, self.Y[n]) for n in self.node_lists]
         if dev.type == "cuda":
             torch.cuda.synchronize()
         self.checksum = [int(g.nnz), int(g.col.sum()), int(torch.round(g.val.double().sum() * 1e3))]
@@ -207,16 +210,6 @@ def build_model(cfg, dev, N, distributed: bool, assign_impl='auto', capacity=Non
     if c["loss"] == "link":
         head = V.LinkPredictor(c["classes"], c["hidden"], 1, 3, 0.0).to(dev).train()
     return model, head
-
-
-def warm_start(model, batches):
-    """The reference's init(): layer-wise feature-only codebook warm start (main_node.py:17-37)."""
-    with torch.no_grad():
-        for layer_idx in range(1, model.num_layers + 1):
-            for x, bA, _ in batches:
-                model.init((x, bA), layer_idx)
-    model.set_inited(True)
-    model.check_status()
 
 
 def loss_fn(cfg, out, y, head=None, plan=None):
@@ -450,7 +443,7 @@ def main():
         if args.cpu_batch:
             c = dict(c, B=args.cpu_batch)
         wl = Workload(c, dev, 0, 1, args.scale, n_batches=1)
-        batch_cpu = batch_to_cpu(wl.batches[0])
+        batch_cpu = batch_to_cpu(wl.make_batch(wl.node_lists[0]))
         del wl
         if dev.type == "cuda":
             torch.cuda.empty_cache()
@@ -522,7 +515,7 @@ def main():
                        "batches_per_pass": ws_batches, "layer_passes": c["layers"] * (c["layers"] + 1) // 2,
                        "what": "LowRankGNN.warm_start = main_node.py init(): untimed for the metric, reported"}
     log(f"[bench] rank {rank}: warm start {warm_start_info['seconds']} s")
-    plans = [model.prepare(b[1]) for b in batches]
+    plans = [model.prepare_from_graph(g, n) for n in wl.node_lists]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib = _lib.load()
 
@@ -740,9 +733,8 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = batches[0]
-        if args.cpu_batch and args.cpu_batch < cb[0].shape[0]:
-            cb = wl.make_batch(wl.node_lists[0][:args.cpu_batch])
+        nb0 = wl.node_lists[0]
+        cb = wl.make_batch(nb0[:args.cpu_batch] if (args.cpu_batch and args.cpu_batch < nb0.numel()) else nb0)
         v, t_step, n_timed, kind, what = cpu_reference_run(c, batch_to_cpu(cb), N, 2, 1, budget_s=120.0)
         cpu_baseline = {"value": v, "unit": "nodes/s/layer", "cores": os.cpu_count(), "kind": kind,
                         "sample": f"{what}: full {c['layers']}-layer train step on one batch of the same workload "
