@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kMpWarps * 32)
 // but every entry's row -- x[c] for a batch column, tail_feat[c - B] otherwise -- is copied global -> shared with
 // cp.async (16 B per lane, no registers held) kAsyncDepth entries ahead of its use, so each warp keeps kAsyncDepth
 // rows in flight instead of kMpUnroll.
-constexpr int kAsyncDepth = 12;
+constexpr int kAsyncDepthDefault = 12;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -124,6 +124,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+template <int kAsyncDepth>
 __global__ void __launch_bounds__(kMpWarps * 32)
     mp_fwd_async_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                         const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks,
@@ -470,11 +471,23 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
   }();
   if (use_async && vec4 && tail_feat && tail_slab == 0 && !rval && feat_scale == 1.0f && C >= 64) {
     // large v2 batch graphs with materialised tail rows: deep cp.async gather pipeline
-    const size_t smem = static_cast<size_t>(kMpWarps) * kAsyncDepth * 32 * 16;
-    VQ_CUDA(cudaFuncSetAttribute(mp_fwd_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mp_fwd_async_kernel<<<grid, kMpWarps * 32, smem, s>>>(rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, R, (int)B,
-                                                          x, ldx, cb, C, nslab, info_scale, y, ldy, info, w.part,
-                                                          w.count, w.p0);
+    static const int depth = []() {
+      const char* e = getenv("VQGNN_ASYNC_DEPTH");
+      const int d = e ? atoi(e) : kAsyncDepthDefault;
+      return (d == 8 || d == 16) ? d : kAsyncDepthDefault;
+    }();
+    const size_t smem = static_cast<size_t>(kMpWarps) * depth * 32 * 16;
+#define VQ_ASYNC(DD)                                                                                              \
+  do {                                                                                                            \
+    VQ_CUDA(cudaFuncSetAttribute(mp_fwd_async_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mp_fwd_async_kernel<DD><<<grid, kMpWarps * 32, smem, s>>>(rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, \
+                                                              R, (int)B, x, ldx, cb, C, nslab, info_scale, y, ldy, \
+                                                              info, w.part, w.count, w.p0);                       \
+  } while (0)
+    if (depth == 8) VQ_ASYNC(8);
+    else if (depth == 16) VQ_ASYNC(16);
+    else VQ_ASYNC(12);
+#undef VQ_ASYNC
     VQ_LAUNCH_CHECK();
     if (n_chunks > 2) {
       mp_fixup_kernel<4><<<grid, kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, y, ldy,
