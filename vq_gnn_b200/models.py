@@ -135,7 +135,7 @@ class VQConvFunction(torch.autograd.Function):
                 # v2: every tail node is referenced by many edges -- gather its codewords once (both halves; the
                 # gradient half is kept for the backward) and let the kernels read coalesced dense rows
                 tail_feat = torch.empty(plan.T, C, device=dev)
-                tail_grad = torch.empty(plan.T, C, device=dev) if need_info else None
+                tail_grad = torch.empty(plan.T, C, device=dev) if (need_info and layer.materialize_grad) else None
                 _lib.check(lib.vqgnn_tail_materialize(
                     _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M,
                     bank.D, bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, st))
@@ -343,6 +343,9 @@ class LowRankGNNLayer(nn.Module):
         # True = when tail nodes are referenced >= 4x on average (measured per layer: arxiv 1.61 -> 1.50 ms, collab
         # 1.59 -> 1.49, products forward 2.09 -> 1.17 + 0.18 ms), 'force' = always, False = never
         self.materialize_tail = True
+        # also materialise the gradient codewords (read by the backward's ~B*deg out-of-batch entries); False: the
+        # backward gathers them per entry from the codebook instead
+        self.materialize_grad = _os.environ.get('VQGNN_MATERIALIZE_GRAD', '1') != '0'
         # v2 training: batch rows and out-of-batch rows (info_backward only) through separate kernels (csrc/mp_info.cu:
         # slab-major tables, L2-resident slices).  True = when the latter hold >= INFO_SPLIT_MIN_ENTRIES entries,
         # 'force' = always, False (default) = never: measured at the products shape both forms run at the same
