@@ -125,7 +125,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 template <int kAsyncDepth>
-__global__ void __launch_bounds__(kMpWarps * 32)
+__global__ void __launch_bounds__(kMpWarps * 32, kAsyncDepth <= 6 ? 8 : 1)
     mp_fwd_async_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                         const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks,
                         int chunk, int nnz, int64_t R, int B, const float* __restrict__ x, int64_t ldx, Codebook cb,
@@ -474,7 +474,7 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
     static const int depth = []() {
       const char* e = getenv("VQGNN_ASYNC_DEPTH");
       const int d = e ? atoi(e) : kAsyncDepthDefault;
-      return (d == 8 || d == 16) ? d : kAsyncDepthDefault;
+      return (d == 4 || d == 6 || d == 8 || d == 16) ? d : kAsyncDepthDefault;
     }();
     const size_t smem = static_cast<size_t>(kMpWarps) * depth * 32 * 16;
 #define VQ_ASYNC(DD)                                                                                              \
@@ -484,7 +484,9 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
                                                               R, (int)B, x, ldx, cb, C, nslab, info_scale, y, ldy, \
                                                               info, w.part, w.count, w.p0);                       \
   } while (0)
-    if (depth == 8) VQ_ASYNC(8);
+    if (depth == 4) VQ_ASYNC(4);
+    else if (depth == 6) VQ_ASYNC(6);
+    else if (depth == 8) VQ_ASYNC(8);
     else if (depth == 16) VQ_ASYNC(16);
     else VQ_ASYNC(12);
 #undef VQ_ASYNC
