@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(256)
   const int lane = threadIdx.x & 31;
   const int task = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (task >= max_tasks || task >= __ldg(task_off + S)) return;
-  int lo = 0, hi = S;   // largest seg with task_off[seg] <= task
+  // largest seg with task_off[seg] <= task.  task_off[seg] = seg + (extra sub-ranges before seg), so the answer lies
+  // in [task - extra_total, task]: a handful of search steps when few segments are long (the common case)
+  const int extra_total = __ldg(task_off + S) - S;
+  int lo = max(0, task - extra_total), hi = min(task, S - 1) + 1;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (__ldg(task_off + mid) <= task) lo = mid;
