@@ -427,3 +427,45 @@ def test_v1_tail_kernel_without_in_batch_block():
     x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
     c_outs = _run_cuda(layer, batch_A, x, 3, dev)
     _compare(c_outs, _run_oracle(o, batch_A, x, 3, cuda_outs=c_outs), layer, o)
+
+
+def test_prefetched_tail_rows_are_bit_identical():
+    """LowRankGNN.prefetch_tails: layers 2..L materialise their out-of-batch codeword rows on a side stream at the start
+    of the forward; training must be bit-identical to materialising in line."""
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    N, B, M, C = 900, 160, 16, 128
+    g = H.make_graph(N, 9000, "GCN", "v2", seed=9)
+    bAs = [H.batch_to(H.make_batch(g, B, "v2", seed=s), dev) for s in range(3)]
+    xs = [torch.randn(B, C, generator=torch.Generator().manual_seed(s)).to(dev) for s in range(3)]
+    ys = [torch.randint(0, 7, (B,), generator=torch.Generator().manual_seed(20 + s)).to(dev) for s in range(3)]
+
+    def run(prefetch, async_vq):
+        torch.manual_seed(0)
+        m = V.LowRankGNN(C, 64, 7, 3, 0., M, 4, N, no_second_fc=True, skip=False, commitment_cost=0.,
+                         grad_scale=[1, 1], act='leaky_gelu', bn_flag=True, warm_up_flag=True, conv_type="GCN",
+                         version="v2").to(dev).train()
+        m.prefetch_tails = prefetch
+        m.set_async_vq_updates(async_vq)
+        for layer in m.convs:
+            layer.materialize_tail = 'force'
+        opt = torch.optim.RMSprop(m.parameters(), lr=1e-3)
+        losses = []
+        for i in range(6):
+            if i == 1:
+                m.set_inited(True)
+            opt.zero_grad()
+            out, _, info = m((xs[i % 3], bAs[i % 3]), 1)
+            loss = F.cross_entropy(out, ys[i % 3]) + info
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+        m.join_vq_updates()
+        torch.cuda.synchronize()
+        return losses, {k: v.clone() for k, v in m.state_dict().items()}
+    l0, s0 = run(False, False)
+    for cfg in ((True, False), (True, True)):
+        l1, s1 = run(*cfg)
+        assert l0 == l1, cfg
+        for k in s0:
+            assert torch.equal(s0[k], s1[k]), (cfg, k)

@@ -129,16 +129,20 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.ptr(iws), st))
         else:
             tail_feat = None
-            auto = plan.nnz >= 4 * plan.T      # tail nodes referenced several times each: gather once, read dense
-            if (not v1 and plan.T > 0 and bank.D == 4 and bank.Wp == 8
-                    and (layer.materialize_tail == 'force' or (layer.materialize_tail and auto))):
+            if layer.wants_dense_tail(plan):
                 # v2: every tail node is referenced by many edges -- gather its codewords once (both halves; the
                 # gradient half is kept for the backward) and let the kernels read coalesced dense rows
-                tail_feat = torch.empty(plan.T, C, device=dev)
-                tail_grad = torch.empty(plan.T, C, device=dev) if (need_info and layer.materialize_grad) else None
-                _lib.check(lib.vqgnn_tail_materialize(
-                    _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M,
-                    bank.D, bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, st))
+                pre = layer._prefetched
+                if pre is not None and pre[0] is plan:        # issued ahead on the side stream (LowRankGNN.forward)
+                    _, tail_feat, tail_grad, ev = pre
+                    layer._prefetched = None
+                    cur = torch.cuda.current_stream(dev)
+                    cur.wait_event(ev)
+                    tail_feat.record_stream(cur)
+                    if tail_grad is not None:
+                        tail_grad.record_stream(cur)
+                else:
+                    tail_feat, tail_grad = layer.materialize_tail_rows(plan, need_info)
                 ctx.tail_grad = tail_grad
             _lib.check(lib.vqgnn_mp_fwd(
                 _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
@@ -352,7 +356,43 @@ class LowRankGNNLayer(nn.Module):
         # ~5.5 TB/s of on-chip gather traffic (1.50 vs 1.60 ms per layer) and the split pays a second small launch for
         # the batch rows (step 9.2 vs 8.5 ms), so the one-kernel forward stays the default
         self.split_info = False
+        self._prefetched = None
         self._restack()
+
+    # ---- dense copies of the out-of-batch codewords (v2) -----------------------------------------
+    def wants_dense_tail(self, plan: BatchPlan) -> bool:
+        bank = self.bank
+        if plan.version != 'v2' or plan.T == 0 or bank.D != 4 or bank.Wp != 8 or self.conv_type == 'GAT':
+            return False
+        return self.materialize_tail == 'force' or bool(self.materialize_tail and plan.nnz >= 4 * plan.T)
+
+    def materialize_tail_rows(self, plan: BatchPlan, with_grad: bool):
+        """tail_feat / tail_grad [T, C]: the feature / gradient codewords of every out-of-batch node (vqgnn_tail_materialize)
+        on the current stream."""
+        bank, dev = self.bank, plan.device
+        C = bank.nb * bank.D
+        tail_feat = torch.empty(plan.T, C, device=dev)
+        tail_grad = torch.empty(plan.T, C, device=dev) if (with_grad and self.materialize_grad) else None
+        _lib.check(_lib.load().vqgnn_tail_materialize(
+            _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
+            bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, _lib.stream()))
+        return tail_feat, tail_grad
+
+    def prefetch_tail_rows(self, plan: BatchPlan, side: "torch.cuda.Stream") -> None:
+        """Issue this layer's materialisation on `side` now (it depends only on the quantiser state and the plan, not
+        on the layer input), to be picked up by the layer's forward: the HBM-write-bound copy then overlaps the
+        gather-bound forward kernels of the layers before it."""
+        self._prefetched = None
+        if not (self.training and plan.training and self.inited and self.wants_dense_tail(plan)
+                and not (self.split_info and self.split_info == 'force')):
+            return
+        self.bank.join()                                   # a pending side-stream VQ update writes codes / O
+        side.wait_stream(torch.cuda.current_stream(plan.device))
+        with torch.cuda.stream(side):
+            tf, tg = self.materialize_tail_rows(plan, True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._prefetched = (plan, tf, tg, ev)
 
     # ---- stacked storage <-> per-branch reference buffers -------------------------------------
     def _restack(self):
@@ -443,6 +483,7 @@ class LowRankGNN(nn.Module):
         self.num_layers, self.skip, self.dropout = num_layers, skip, dropout
         self.bn_flag, self.alpha_dropout_flag = bn_flag, alpha_dropout_flag
         self.version, self.conv_type, self.num_N = version, conv_type, num_N
+        self.prefetch_tails = True      # v2 training: see LowRankGNNLayer.prefetch_tail_rows
         if self.alpha_dropout_flag:
             self.alpha_dropout = nn.AlphaDropout(p=self.dropout)
         self.convs, self.batch_norms = nn.ModuleList(), nn.ModuleList()
@@ -497,6 +538,12 @@ class LowRankGNN(nn.Module):
         errors_full, X_B_norms_full, quantized_norms_full = [], [], []
         x, batch_A = batch
         batch_A = build_plan(batch_A, self.conv_type, self.num_N, self.training, x.device)
+        if (self.prefetch_tails and self.training and not unlabeled and x.is_cuda and self.version == 'v2'
+                and len(self.convs) > 1):
+            # layers 2..L: materialise their out-of-batch codeword rows on a side stream while layer 1 runs
+            side = VQBank.side_stream(x.device, 1)
+            for conv in self.convs[1:]:
+                conv.prefetch_tail_rows(batch_A, side)
         for i, conv in enumerate(self.convs[:-1]):
             x, errors, X_B_norms, quantized_norms, losses, info_backwards, _ = \
                 conv(x, batch_A, warm_up_rate, unlabeled)

@@ -240,10 +240,11 @@ class VQBank:
     _SIDE = {}
 
     @classmethod
-    def side_stream(cls, dev) -> "torch.cuda.Stream":
-        """ONE side stream per device, shared by every bank: the updates (and their collectives) of all layers stay in
-        program order, which is the same on every rank."""
-        key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    def side_stream(cls, dev, which: int = 0) -> "torch.cuda.Stream":
+        """ONE side stream per device (and purpose: 0 = VQ updates, 1 = tail-row prefetch), shared by every bank: the
+        updates (and their collectives) of all layers stay in program order, which is the same on every rank."""
+        idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+        key = (idx, which)
         st = cls._SIDE.get(key)
         if st is None:
             st = cls._SIDE[key] = torch.cuda.Stream(device=dev)
