@@ -136,11 +136,7 @@ class VQConvFunction(torch.autograd.Function):
                 if pre is not None and pre[0] is plan:        # issued ahead on the side stream (LowRankGNN.forward)
                     _, tail_feat, tail_grad, ev = pre
                     layer._prefetched = None
-                    cur = torch.cuda.current_stream(dev)
-                    cur.wait_event(ev)
-                    tail_feat.record_stream(cur)
-                    if tail_grad is not None:
-                        tail_grad.record_stream(cur)
+                    torch.cuda.current_stream(dev).wait_event(ev)
                 else:
                     tail_feat, tail_grad = layer.materialize_tail_rows(plan, need_info)
                 ctx.tail_grad = tail_grad
@@ -366,13 +362,16 @@ class LowRankGNNLayer(nn.Module):
             return False
         return self.materialize_tail == 'force' or bool(self.materialize_tail and plan.nnz >= 4 * plan.T)
 
-    def materialize_tail_rows(self, plan: BatchPlan, with_grad: bool):
+    def materialize_tail_rows(self, plan: BatchPlan, with_grad: bool, out=None):
         """tail_feat / tail_grad [T, C]: the feature / gradient codewords of every out-of-batch node (vqgnn_tail_materialize)
-        on the current stream."""
+        on the current stream (into `out` = (tail_feat, tail_grad) when given)."""
         bank, dev = self.bank, plan.device
         C = bank.nb * bank.D
-        tail_feat = torch.empty(plan.T, C, device=dev)
-        tail_grad = torch.empty(plan.T, C, device=dev) if (with_grad and self.materialize_grad) else None
+        if out is None:
+            tail_feat = torch.empty(plan.T, C, device=dev)
+            tail_grad = torch.empty(plan.T, C, device=dev) if (with_grad and self.materialize_grad) else None
+        else:
+            tail_feat, tail_grad = out
         _lib.check(_lib.load().vqgnn_tail_materialize(
             _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
             bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, _lib.stream()))
@@ -387,9 +386,14 @@ class LowRankGNNLayer(nn.Module):
                 and not (self.split_info and self.split_info == 'force')):
             return
         self.bank.join()                                   # a pending side-stream VQ update writes codes / O
+        # the buffers are allocated on the CONSUMER's stream (its allocator pool owns them; the side stream's writes are
+        # ordered before the consumer's reads by the event), so no cross-stream record_stream bookkeeping is needed
+        C = self.bank.nb * self.bank.D
+        tf = torch.empty(plan.T, C, device=plan.device)
+        tg = torch.empty(plan.T, C, device=plan.device) if self.materialize_grad else None
         side.wait_stream(torch.cuda.current_stream(plan.device))
         with torch.cuda.stream(side):
-            tf, tg = self.materialize_tail_rows(plan, True)
+            self.materialize_tail_rows(plan, True, out=(tf, tg))
             ev = torch.cuda.Event()
             ev.record(side)
         self._prefetched = (plan, tf, tg, ev)
