@@ -8,7 +8,7 @@ LIB := vq_gnn_b200/libvqgnn.so
 
 all: $(LIB)
 
-%.o: %.cu vq_gnn_b200/csrc/common.cuh vq_gnn_b200/csrc/mp_common.cuh include/vqgnn.h
+%.o: %.cu $(wildcard vq_gnn_b200/csrc/*.cuh) include/vqgnn.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(OBJ)

@@ -248,6 +248,8 @@ def algorithmic_work(kernel: str, plan, C: int, nb: int, M: int, B: int):
         return nnz_o * 8 + (plan.T + 1) * 4 + plan.T * nb * 2 + 2 * M * C * 4 + B * C * 4, "hbm"
     if kernel == "vqgnn_tail_materialize_slab":
         return plan.T * nb * 2 + 2 * plan.T * C * 4 + 2 * M * C * 4, "hbm"
+    if kernel == "vqgnn_mp_fwd_rows":   # same compulsory bytes as the forward it replaces
+        kernel = "vqgnn_mp_fwd"
     if kernel in ("vqgnn_mp_fwd", "vqgnn_gat_fwd"):
         if not v1 and plan.extras.get('split_fwd') and kernel == "vqgnn_mp_fwd":   # batch rows only (split forward)
             nB = plan.nnz_B

@@ -166,6 +166,18 @@ int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, co
                  float info_scale, float* y, int64_t ldy, float* gq, int64_t ldgq, float* info, void* ws,
                  void* stream);
 
+/* The same forward for batch graphs whose out-of-batch codeword rows were materialised (vqgnn_tail_materialize):
+ * every entry's row -- x[col] for a batch column, tail_feat[col - B] otherwise -- is fetched by one TMA bulk copy
+ * (cp.async.bulk, <= 512 B per 128-column slab) into a per-warp ring of shared memory, so the consuming loop holds no
+ * address arithmetic (csrc/mp_rows.cuh).  rows r < B: y[r] = acc; rows r >= B: info += <acc, tail_grad[r - B]>
+ * (vq_gnn_v2/models.py:161-198).  Replaces vqgnn_mp_fwd(rval = NULL, tail_slab = 0, feat_scale = 1) with identical
+ * per-row arithmetic; needs C >= 64, C % 4 == 0, chunk <= 256, 16 B aligned rows.  tail_feat may be NULL when R == B
+ * and every column is < B (plain convolution); tail_grad may be NULL when info is.  ws as for vqgnn_mp_fwd. */
+int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* chunk_row,
+                      int chunk, int64_t nnz, int64_t R, int64_t B, const float* x, int64_t ldx,
+                      const float* tail_feat, const float* tail_grad, int64_t ld_tail, int C, float info_scale,
+                      float* y, int64_t ldy, float* info, void* ws, void* stream);
+
 /* Dense copies of the tail entries' codewords: tail_feat[t, 4k:4k+4] = O_k[code_k(node(t)), :4],
  * tail_grad[t, 4k:4k+4] = O_k[code_k(node(t)), 4:8] (either may be NULL; D == 4, Wp == 8).  In a v2 batch graph
  * a tail node is referenced by ~20 edges: gathering its codewords once and handing the rows to vqgnn_mp_fwd

@@ -15,9 +15,11 @@
 //
 // Reference maths: vq_gnn_v2/models.py:161-198, vq_gnn_v2/convs.py:65-101,
 // vq_gnn_v1/models.py:170-223 + vq_gnn_v1/utils/dataloader.py:144-192.
+#include <algorithm>
 #include <cstdlib>
 
 #include "mp_common.cuh"
+#include "mp_rows.cuh"
 
 namespace vqgnn {
 
@@ -379,7 +381,7 @@ static size_t mp_ws_layout(void* ws, int64_t nnz, int chunk, int C, MpWs* out) {
   const int vec = 4;   // upper bound of the grid: the VEC = 1 variant has more slabs, sized for it below
   (void)vec;
   const int64_t nslab1 = (C + 31) / 32;
-  const size_t grid_max = static_cast<size_t>((n_chunks * nslab1 + kMpWarps - 1) / kMpWarps) + 1;
+  const size_t grid_max = static_cast<size_t>(n_chunks * nslab1) + 1;   // >= the grid of every forward variant
   const size_t pieces = mp_al256(static_cast<size_t>(n_chunks) * 2 * C * sizeof(float));
   char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255));
   if (out) {
@@ -519,6 +521,59 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
     else
       mp_fixup_kernel<1><<<grid, kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C, nslab, w.p0, y, ldy,
                                                         pq, gq, ldgq);
+    VQ_LAUNCH_CHECK();
+  }
+  return VQGNN_OK;
+}
+
+extern "C" int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, const float* val,
+                                 const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
+                                 const float* x, int64_t ldx, const float* tail_feat, const float* tail_grad,
+                                 int64_t ld_tail, int C, float info_scale, float* y, int64_t ldy, float* info,
+                                 void* ws, void* stream) {
+  VQ_CHECK_ARG(rowptr && x && y && (nnz == 0 || (col && val)), "mp_fwd_rows: null argument");
+  VQ_CHECK_ARG(R >= B && B > 0 && B < (1ll << 31) && R < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31),
+               "mp_fwd_rows: bad sizes");
+  VQ_CHECK_ARG(R == B || tail_feat, "mp_fwd_rows: out-of-batch columns need the materialised feature rows (tail_feat)");
+  VQ_CHECK_ARG(!info || R == B || tail_grad, "mp_fwd_rows: info needs the materialised gradient rows (tail_grad)");
+  VQ_CHECK_ARG(C >= 64 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ld_tail % 4 == 0 && aligned16(x) &&
+                   aligned16(y) && (!tail_feat || aligned16(tail_feat)) && (!tail_grad || aligned16(tail_grad)),
+               "mp_fwd_rows: needs C >= 64, C % 4 == 0 and 16 B aligned rows");
+  VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && chunk <= kRowsChunkMax && (nnz == 0 || chunk_row),
+               "mp_fwd_rows: needs chunk_row (vqgnn_mp_chunk_rows) with chunk <= 256");
+  VQ_CHECK_ARG(ws || nnz == 0, "mp_fwd_rows: needs a workspace of vqgnn_mp_workspace_bytes(nnz, chunk, C) bytes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MpWs w{nullptr, nullptr, nullptr, nullptr};
+  if (ws) mp_ws_layout(ws, nnz, chunk, C, &w);
+  if (info && ws) VQ_CUDA(cudaMemsetAsync(w.count, 0, 16, s));
+  if (int rc = zero_rows(y, B, C, ldy, s)) return rc;
+  const int n_chunks = static_cast<int>(vqgnn_mp_num_chunks(nnz, chunk));
+  if (n_chunks == 0) {
+    if (info) VQ_CUDA(cudaMemsetAsync(info, 0, sizeof(float), s));
+    return VQGNN_OK;
+  }
+  const int nslab = ceil_div(C, 128);
+  const int64_t tasks = static_cast<int64_t>(n_chunks) * nslab;
+  // 32-bit row offsets (16 B units) from a common base below both tables
+  const uintptr_t xa = reinterpret_cast<uintptr_t>(x), ta = tail_feat ? reinterpret_cast<uintptr_t>(tail_feat) : xa;
+  const uintptr_t base = std::min(xa, ta);
+  const uint64_t x_end4 = (xa - base) / 16 + static_cast<uint64_t>(B) * (ldx / 4) + 32;
+  const uint64_t t_end4 = (ta - base) / 16 + static_cast<uint64_t>(R - B) * (ld_tail / 4) + 32;
+  VQ_CHECK_ARG(x_end4 < (1ull << 32) && t_end4 < (1ull << 32),
+               "mp_fwd_rows: x and tail_feat must lie within 64 GB of each other (32-bit row offsets)");
+  // warps per CTA x ring slots, measured at the products shape (16 M entries, C = 128): 4 x 8 -> 0.90 ms per launch,
+  // 8 x 8 0.98, 2 x 8 0.97, 1 x 8 1.05, 4 x 16 0.97, 8 x 4 1.11, 4 x 32 1.54 (mp_fwd_async_kernel: 1.36)
+  constexpr int NW = kRowsWarps, SLOTS = kRowsSlots;
+  const size_t smem = sizeof(RowsWarpSmem<SLOTS>) * NW;
+  mp_fwd_rows_kernel<NW, SLOTS><<<ceil_div(tasks, NW), NW * 32, smem, s>>>(
+      rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, (int)R, (int)B, reinterpret_cast<const float4*>(base),
+      static_cast<uint32_t>((xa - base) / 16), static_cast<uint32_t>(ldx / 4), static_cast<uint32_t>((ta - base) / 16),
+      static_cast<uint32_t>(ld_tail / 4), tail_grad, ld_tail, C, nslab, info_scale, y, ldy, info, w.part, w.count,
+      w.p0);
+  VQ_LAUNCH_CHECK();
+  if (n_chunks > 2) {   // rows spanning >= 3 chunks: ordered sum of their pieces
+    mp_fixup_kernel<4><<<ceil_div(tasks, kMpWarps), kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C,
+                                                                         nslab, w.p0, y, ldy, nullptr, nullptr, 0);
     VQ_LAUNCH_CHECK();
   }
   return VQGNN_OK;

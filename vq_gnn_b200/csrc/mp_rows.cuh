@@ -1,0 +1,225 @@
+// v2 forward of large batch graphs with materialised codeword rows: lean asynchronous row gathers.
+//
+// csrc/mp.cu's mp_fwd_async_kernel was ISSUE bound (ncu, products shape: 84 warp instructions per CSR entry, 89 % of the
+// issue slots busy, L2 at 45 %, DRAM at 34 %): the sequential row walk, the per-entry address arithmetic and one
+// commit / wait pair per entry.  Same work partition here (warp x 256-entry CSR chunk x 128-column slab), same in-order
+// accumulation and the same order-independent piece scheme as mp_fwd_kernel, but
+//   * a warp owns a small ring of row slots (kRowsSlots = 8 x 512 B) in four cp.async groups; entry n of the chunk uses
+//     slot n % 8, and a group is refilled (16 B per lane, one commit per group, one wait per group) as soon as it has
+//     been consumed: 6..8 rows in flight per warp, 28 warps per SM.  Measured: small rings with many warps beat deep
+//     rings (32 slots x 12 warps: 1.54 ms, 8 slots x 28 warps: 0.90 ms per launch at the products shape);
+//   * every lane precomputes the 32-bit offset (in 16 B units from a common base) of ITS entry's row once per batch, so
+//     issuing a row is SHFL + IADD + IMAD.WIDE + LDGSTS;
+//   * row ends are marked once per task from the row pointers (a 256-bit mask + the row id of every end position in
+//     shared memory), so the fully unrolled consuming loop costs one predicate test per entry instead of the sequential
+//     row walk: SHFL (value) + LDS.128 + 4 FFMA + test;
+//   * the gradient codeword row of an out-of-batch row (the other operand of info_backward) is read from the
+//     materialised table and prefetched one row ahead.
+// Tried first and dropped: one `cp.async.bulk` (TMA) per row completing on an mbarrier -- correct but slower than the
+// kernel it was to replace (1.59 vs 1.36 ms): 512 B bulk copies are bound by the per-SM TMA request rate (~1 per 29 clk).
+//
+// Reference maths: vq_gnn_v2/models.py:161-198 (conv over [x ; codewords], info_backward), vq_gnn_v2/convs.py:65-101.
+#pragma once
+#include "mp_common.cuh"
+
+namespace vqgnn {
+
+constexpr int kRowsChunkMax = 256;   // entries per task (the plan's MP_CHUNK)
+constexpr int kRowsSlotBytes = 512;  // one slab of a row: 128 fp32 columns
+constexpr int kRowsWarps = 4;        // warps per CTA
+constexpr int kRowsSlots = 8;        // ring slots (rows in flight) per warp: four cp.async groups of two
+
+template <int SLOTS>
+struct __align__(128) RowsWarpSmem {
+  float4 ring[SLOTS * 32];           // SLOTS x 512 B
+  int32_t row_of[kRowsChunkMax];     // row id of every row-end position of the task
+  uint32_t endmask[kRowsChunkMax / 32];
+};
+
+__device__ __forceinline__ uint32_t rows_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void rows_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void rows_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rows_cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// per-block fp64 partial of the info scalar, blocks added in index order by the last block (cf. info_reduce_ordered)
+template <int NW>
+__device__ __forceinline__ void rows_info_reduce(double part, double* ws_part, unsigned int* ws_count,
+                                                 float info_scale, float* info) {
+  __shared__ double sh[NW];
+  __shared__ bool last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  part = warp_sum(part);
+  if (lane == 0) sh[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) t += sh[i];
+    ws_part[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(ws_count, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double t = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += __ldcg(ws_part + i);
+  t = warp_sum(t);
+  __syncthreads();
+  if (lane == 0) sh[warp] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) total += sh[i];
+    *info = static_cast<float>(static_cast<double>(info_scale) * total);
+  }
+}
+
+// base: a 16 B aligned address below both tables; xoff4 / toff4: offsets of x / tail_feat from it in 16 B units;
+// ldx4 / ldt4: row strides in 16 B units.  Every gathered piece must lie below base + 2^32 * 16 B (checked on the host).
+template <int NW, int SLOTS>
+__global__ void __launch_bounds__(NW * 32)
+    mp_fwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
+                       int nnz, int R, int B, const float4* __restrict__ base, uint32_t xoff4, uint32_t ldx4,
+                       uint32_t toff4, uint32_t ldt4, const float* __restrict__ tail_grad, int64_t ld_tail, int C,
+                       int nslab, float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ info,
+                       double* ws_part, unsigned int* ws_count, float* __restrict__ py) {
+  extern __shared__ __align__(128) unsigned char rows_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RowsWarpSmem<SLOTS>& S = reinterpret_cast<RowsWarpSmem<SLOTS>*>(rows_smem)[warp];
+  constexpr int G = SLOTS / 4;       // rows per cp.async group; four groups in flight
+  const int64_t task = static_cast<int64_t>(blockIdx.x) * NW + warp;
+  float fpart = 0.f;
+  if (task < static_cast<int64_t>(n_chunks) * nslab) {
+    const int slab = static_cast<int>(task / n_chunks);
+    const int ch = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
+    const int c0 = slab * 128 + lane * 4;        // the lane's four columns
+    const bool active = c0 < C;
+    const int eb = ch * chunk, ee = min(eb + chunk, nnz);
+    const int row0 = __ldg(chunk_row + ch);
+    const int rowL = ch + 1 < n_chunks ? __ldg(chunk_row + ch + 1) : R - 1;   // row of the first entry after the chunk
+    const uint32_t slot_s = rows_smem_u32(S.ring) + lane * 16;                // the lane's 16 B of slot 0
+
+    if (lane < kRowsChunkMax / 32) S.endmask[lane] = 0u;
+    __syncwarp();
+    // row ends inside the chunk: bit p of the mask <=> entry eb + p is the last entry of row row_of[p]
+    for (int r = row0 + lane; r <= rowL; r += 32) {
+      const int rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+      if (re > rs && re > eb && re <= ee) {
+        const int p = re - 1 - eb;
+        atomicOr(&S.endmask[p >> 5], 1u << (p & 31));
+        S.row_of[p] = r;
+      }
+    }
+    const bool row0_starts_here = __ldg(rowptr + row0) >= eb;
+    __syncwarp();
+
+    // entries: lane l of batch b holds entry eb + 32 b + l (value + row offset); two batches in registers
+    uint32_t o_cur, o_nxt;
+    float v_cur, v_nxt;
+    const uint32_t lane_off = static_cast<uint32_t>(slab * 32);
+    auto load_batch = [&](int bb, uint32_t& o_l, float& v_l) {
+      const int e = bb + lane;
+      o_l = 0u, v_l = 0.f;
+      if (e < ee) {
+        const int c = __ldg(col + e);
+        v_l = __ldg(val + e);
+        o_l = (c >= B ? toff4 + static_cast<uint32_t>(c - B) * ldt4 : xoff4 + static_cast<uint32_t>(c) * ldx4) + lane_off;
+      }
+    };
+    // entry n of the chunk uses ring slot n % SLOTS.  refill(j0, ...): issue the G entries that follow the entries
+    // j0 .. j0+G-1 of the current batch by SLOTS positions (they reuse the slots just consumed); their row offsets are
+    // in o_a (same batch) or o_b (next batch).  Always one commit, so that the consumer's wait counts groups.
+    auto refill = [&](int j0, uint32_t o_a, uint32_t o_b, int bb) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const int j = j0 + u + SLOTS;      // position relative to the current batch
+        const uint32_t o = __shfl_sync(0xffffffffu, j < 32 ? o_a : o_b, j & 31) + lane;
+        if (bb + j < ee && active) rows_cp_async16(slot_s + (j % SLOTS) * kRowsSlotBytes, base + o);
+      }
+      rows_cp_commit();
+    };
+    load_batch(eb, o_cur, v_cur);
+    load_batch(eb + 32, o_nxt, v_nxt);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) refill(g * G - SLOTS, o_cur, o_nxt, eb);
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // gradient codeword row of the next out-of-batch row, prefetched (rows >= B are consecutive tail entries)
+    int r_pref = row0;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_gv = [&](int r) {
+      if (info && active && r >= B && r < R)
+        gv = __ldg(reinterpret_cast<const float4*>(tail_grad + static_cast<int64_t>(r - B) * ld_tail + c0));
+    };
+    load_gv(r_pref);
+
+    auto flush = [&](int r, bool whole) {
+      if (r != r_pref) load_gv(r);
+      if (active) {
+        if (r < B) {
+          float* yp = y + static_cast<int64_t>(r) * ldy + c0;
+          if (whole) {
+            st_vec<4>(yp, acc);
+          } else {
+            const int kind = piece_kind(false, __ldg(rowptr + r), __ldg(rowptr + r + 1), eb, chunk);
+            if (kind == kPieceRed) red_vec<4>(yp, acc);
+            else st_vec<4>(py + (static_cast<int64_t>(ch) * 2 + (kind == kPieceHubStart ? 1 : 0)) * C + c0, acc);
+          }
+        } else if (info) {   // v2: <Y[r], Gq[r]> with Gq the node's own gradient codeword (models.py:198)
+          fpart = fmaf(acc[0], gv.x, fpart), fpart = fmaf(acc[1], gv.y, fpart);
+          fpart = fmaf(acc[2], gv.z, fpart), fpart = fmaf(acc[3], gv.w, fpart);
+        }
+      }
+      r_pref = r + 1;
+      load_gv(r_pref);
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    };
+
+    int batch = 0;
+    for (int bb = eb; bb < ee; bb += 32, ++batch) {
+      const int cnt = min(32, ee - bb);
+      const uint32_t em = S.endmask[batch];
+#pragma unroll
+      for (int g = 0; g < 32 / G; ++g) {
+        rows_cp_wait<3>();         // the oldest of the four groups in flight = entries gG .. gG+G-1 of this batch
+        if (G * g < cnt) {
+#pragma unroll
+          for (int u = 0; u < G; ++u) {
+            const int j = G * g + u;
+            if (j < cnt) {
+              const float v = __shfl_sync(0xffffffffu, v_cur, j);
+              if (active) {
+                const float4 a = S.ring[(j % SLOTS) * 32 + lane];
+                acc[0] = fmaf(v, a.x, acc[0]), acc[1] = fmaf(v, a.y, acc[1]);
+                acc[2] = fmaf(v, a.z, acc[2]), acc[3] = fmaf(v, a.w, acc[3]);
+              }
+              if ((em >> j) & 1u) {
+                const int r = S.row_of[batch * 32 + j];
+                flush(r, r != row0 || row0_starts_here);
+              }
+            }
+          }
+        }
+        refill(G * g, o_cur, o_nxt, bb);   // a lane refills only the 16 B it has just read itself
+      }
+      o_cur = o_nxt, v_cur = v_nxt;
+      load_batch(bb + 64, o_nxt, v_nxt);
+    }
+    rows_cp_wait<0>();
+    const int pl = ee - 1 - eb;
+    if (!((S.endmask[pl >> 5] >> (pl & 31)) & 1u)) flush(rowL, false);   // trailing part of a row cut by the chunk end
+  }
+  if (info) rows_info_reduce<NW>(static_cast<double>(fpart), ws_part, ws_count, info_scale, info);
+}
+
+}  // namespace vqgnn

@@ -29,6 +29,7 @@ from .graph import MP_CHUNK, TAIL_CHUNK, TAIL_MIN_AVG_DEGREE, BatchPlan, CSRAdj,
 
 import os as _os
 INFO_SLAB = int(_os.environ.get('VQGNN_INFO_SLAB', '16'))     # columns per slab of the split info kernel (16/32/64)
+USE_ROWS_KERNEL = _os.environ.get('VQGNN_MPFWD_ROWS', '1') != '0'   # TMA row-gather forward (csrc/mp_rows.cuh)
 INFO_SPLIT_MIN_ENTRIES = 1 << 20     # below this the one-kernel forward is as fast
 from .vq import VectorQuantizerEMA, VQBank
 
@@ -140,14 +141,23 @@ class VQConvFunction(torch.autograd.Function):
                 else:
                     tail_feat, tail_grad = layer.materialize_tail_rows(plan, need_info)
                 ctx.tail_grad = tail_grad
-            _lib.check(lib.vqgnn_mp_fwd(
-                _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
-                _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
-                _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
-                _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C, 0,
-                float(wu) if v1 else 1.0, float(wu),
-                _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
-                _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
+            if (tail_feat is not None and not v1 and USE_ROWS_KERNEL and C >= 64 and C % 4 == 0 and x.stride(0) % 4 == 0
+                    and (tail_grad is not None or not need_info)):
+                # materialised rows: TMA row gathers (csrc/mp_rows.cuh)
+                _lib.check(lib.vqgnn_mp_fwd_rows(
+                    _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
+                    _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
+                    _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, C, float(wu), _lib.ptr(y), y.stride(0),
+                    _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
+            else:
+                _lib.check(lib.vqgnn_mp_fwd(
+                    _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val), _lib.ptr(plan.fwd_rval),
+                    _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
+                    _lib.ptr(plan.tail_node), _lib.ptr(bank.codes),
+                    _lib.ptr(bank.O), bank.nb, bank.M, bank.D, bank.Wp, _lib.ptr(tail_feat), C, 0,
+                    float(wu) if v1 else 1.0, float(wu),
+                    _lib.ptr(y), y.stride(0), _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
+                    _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
         ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook = layer, plan, float(wu), fire_hook
         if not hasattr(ctx, 'tail_grad'):
             ctx.tail_grad = None
