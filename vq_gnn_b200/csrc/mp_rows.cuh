@@ -48,6 +48,19 @@ __device__ __forceinline__ void rows_cp_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// compile-time loop: f(IntC<I>) for I in [I0, I1)
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+template <int I0, int I1, class F>
+__device__ __forceinline__ void constexpr_for(F&& f) {
+  if constexpr (I0 < I1) {
+    f(IntC<I0>{});
+    constexpr_for<I0 + 1, I1>(f);
+  }
+}
+
 // per-block fp64 partial of the info scalar, blocks added in index order by the last block (cf. info_reduce_ordered)
 template <int NW>
 __device__ __forceinline__ void rows_info_reduce(double part, double* ws_part, unsigned int* ws_count,
@@ -136,22 +149,29 @@ __global__ void __launch_bounds__(NW * 32)
         o_l = (c >= B ? toff4 + static_cast<uint32_t>(c - B) * ldt4 : xoff4 + static_cast<uint32_t>(c) * ldx4) + lane_off;
       }
     };
-    // entry n of the chunk uses ring slot n % SLOTS.  refill(j0, ...): issue the G entries that follow the entries
-    // j0 .. j0+G-1 of the current batch by SLOTS positions (they reuse the slots just consumed); their row offsets are
-    // in o_a (same batch) or o_b (next batch).  Always one commit, so that the consumer's wait counts groups.
-    auto refill = [&](int j0, uint32_t o_a, uint32_t o_b, int bb) {
+    // entry n of the chunk uses ring slot n % SLOTS.  refill<S0>(j0, o_src, bb): issue the G entries that sit SLOTS
+    // positions after the entries j0 .. j0+G-1 of the current batch (they reuse the slots S0 .. S0+G-1 just consumed);
+    // o_src holds their row offsets (the current batch's register, or the next batch's when j0 + SLOTS >= 32).  Always
+    // one commit, so that the consumer's wait counts groups.
+    auto refill = [&](auto s0_tag, int j0, uint32_t o_src, int bb) {
+      constexpr int S0 = decltype(s0_tag)::value;
 #pragma unroll
       for (int u = 0; u < G; ++u) {
-        const int j = j0 + u + SLOTS;      // position relative to the current batch
-        const uint32_t o = __shfl_sync(0xffffffffu, j < 32 ? o_a : o_b, j & 31) + lane;
-        if (bb + j < ee && active) rows_cp_async16(slot_s + (j % SLOTS) * kRowsSlotBytes, base + o);
+        const int j = j0 + u + SLOTS;      // position relative to the current batch (may reach into the next one)
+        const uint32_t o = __shfl_sync(0xffffffffu, o_src, j & 31) + lane;
+        if (bb + j < ee && active) rows_cp_async16(slot_s + (S0 + u) * kRowsSlotBytes, base + o);
       }
       rows_cp_commit();
     };
     load_batch(eb, o_cur, v_cur);
     load_batch(eb + 32, o_nxt, v_nxt);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) refill(g * G - SLOTS, o_cur, o_nxt, eb);
+    static_assert(SLOTS == 4 * G && 32 % SLOTS == 0, "ring = four groups; a batch is a whole number of ring rounds");
+    {   // prologue: the first SLOTS entries
+      constexpr_for<0, 4>([&](auto gt) {
+        constexpr int g = decltype(gt)::value;
+        refill(IntC<g * G>{}, g * G - SLOTS, o_cur, eb);
+      });
+    }
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     // gradient codeword row of the next out-of-batch row, prefetched (rows >= B are consecutive tail entries)
@@ -185,32 +205,40 @@ __global__ void __launch_bounds__(NW * 32)
       acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
     };
 
+    // The consuming loop is unrolled over ONE ring round (SLOTS entries: static slot addresses), not over the batch:
+    // with the row flush inlined 32 times the kernel was 120-150 KB of SASS and its speed followed the code size
+    // (instruction cache), not the algorithm.
     int batch = 0;
     for (int bb = eb; bb < ee; bb += 32, ++batch) {
       const int cnt = min(32, ee - bb);
       const uint32_t em = S.endmask[batch];
+#pragma unroll 1
+      for (int j0 = 0; j0 < 32; j0 += SLOTS) {     // ring rounds of this batch
+        const uint32_t emr = em >> j0;
+        const uint32_t o_src = (j0 + SLOTS < 32) ? o_cur : o_nxt;
+        constexpr_for<0, 4>([&](auto gt) {
+          constexpr int g = decltype(gt)::value;
+          rows_cp_wait<3>();       // the oldest of the four groups in flight = this round's group g
+          if (j0 + g * G < cnt) {
 #pragma unroll
-      for (int g = 0; g < 32 / G; ++g) {
-        rows_cp_wait<3>();         // the oldest of the four groups in flight = entries gG .. gG+G-1 of this batch
-        if (G * g < cnt) {
-#pragma unroll
-          for (int u = 0; u < G; ++u) {
-            const int j = G * g + u;
-            if (j < cnt) {
-              const float v = __shfl_sync(0xffffffffu, v_cur, j);
-              if (active) {
-                const float4 a = S.ring[(j % SLOTS) * 32 + lane];
-                acc[0] = fmaf(v, a.x, acc[0]), acc[1] = fmaf(v, a.y, acc[1]);
-                acc[2] = fmaf(v, a.z, acc[2]), acc[3] = fmaf(v, a.w, acc[3]);
-              }
-              if ((em >> j) & 1u) {
-                const int r = S.row_of[batch * 32 + j];
-                flush(r, r != row0 || row0_starts_here);
+            for (int u = 0; u < G; ++u) {
+              const int s = g * G + u;              // ring slot (a constant after unrolling)
+              if (j0 + s < cnt) {
+                const float v = __shfl_sync(0xffffffffu, v_cur, j0 + s);
+                if (active) {
+                  const float4 a = S.ring[s * 32 + lane];
+                  acc[0] = fmaf(v, a.x, acc[0]), acc[1] = fmaf(v, a.y, acc[1]);
+                  acc[2] = fmaf(v, a.z, acc[2]), acc[3] = fmaf(v, a.w, acc[3]);
+                }
+                if ((emr >> s) & 1u) {
+                  const int r = S.row_of[batch * 32 + j0 + s];
+                  flush(r, r != row0 || row0_starts_here);
+                }
               }
             }
           }
-        }
-        refill(G * g, o_cur, o_nxt, bb);   // a lane refills only the 16 B it has just read itself
+          refill(IntC<g * G>{}, j0 + g * G, o_src, bb);   // a lane refills only the 16 B it has read itself
+        });
       }
       o_cur = o_nxt, v_cur = v_nxt;
       load_batch(bb + 64, o_nxt, v_nxt);
