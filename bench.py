@@ -248,8 +248,10 @@ def algorithmic_work(kernel: str, plan, C: int, nb: int, M: int, B: int):
         return nnz_o * 8 + (plan.T + 1) * 4 + plan.T * nb * 2 + 2 * M * C * 4 + B * C * 4, "hbm"
     if kernel == "vqgnn_tail_materialize_slab":
         return plan.T * nb * 2 + 2 * plan.T * C * 4 + 2 * M * C * 4, "hbm"
-    if kernel == "vqgnn_mp_fwd_rows":   # same compulsory bytes as the forward it replaces
+    if kernel == "vqgnn_mp_fwd_rows":   # same compulsory bytes as the generic forward / backward it replaces
         kernel = "vqgnn_mp_fwd"
+    if kernel == "vqgnn_mp_fwd_rows:bwd":
+        kernel = "vqgnn_mp_bwd"
     if kernel in ("vqgnn_mp_fwd", "vqgnn_gat_fwd"):
         if not v1 and plan.extras.get('split_fwd') and kernel == "vqgnn_mp_fwd":   # batch rows only (split forward)
             nB = plan.nnz_B
@@ -709,9 +711,12 @@ def main():
     work, bound = 0.0, "hbm"
     for i in range(n_attr):
         plan_i = plans[i % len(plans)]
-        for cin in dims:
+        for li, cin in enumerate(dims):
             w_, bound = algorithmic_work(top, plan_i, cin, cin // c["D"], c["M"], plan_i.B)
             work += w_
+            if top == "vqgnn_mp_fwd_rows" and li > 0 and plan_i.version == 'v2':
+                # the v2 backward of layers 2..L runs through the same entry point (transposed CSR): count its bytes
+                work += algorithmic_work("vqgnn_mp_fwd_rows:bwd", plan_i, cin, cin // c["D"], c["M"], plan_i.B)[0]
     n_launch, ms_total = summ[top]
     avg_ms = ms_total / n_launch
     per_launch_work = work / n_launch

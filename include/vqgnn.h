@@ -172,11 +172,16 @@ int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, co
  * address arithmetic (csrc/mp_rows.cuh).  rows r < B: y[r] = acc; rows r >= B: info += <acc, tail_grad[r - B]>
  * (vq_gnn_v2/models.py:161-198).  Replaces vqgnn_mp_fwd(rval = NULL, tail_slab = 0, feat_scale = 1) with identical
  * per-row arithmetic; needs C >= 64, C % 4 == 0, chunk <= 256, 16 B aligned rows.  tail_feat may be NULL when R == B
- * and every column is < B (plain convolution); tail_grad may be NULL when info is.  ws as for vqgnn_mp_fwd. */
+ * and every column is < B (plain convolution); tail_grad may be NULL when info is.  ws as for vqgnn_mp_fwd.
+ * The value of an entry whose column is >= B is multiplied by tail_scale * (tail_scale_dev ? *tail_scale_dev : 1)
+ * (forward: 1, NULL).  That makes the v2 BACKWARD the same call over the transposed CSR of the batch columns:
+ * x = dY, tail_feat = the gradient codeword rows, tail_scale = warm-up rate, tail_scale_dev = d info (device scalar),
+ * R = B, info = NULL  ==  vqgnn_mp_bwd(gq = NULL) with the same per-element arithmetic.  T = rows of tail_feat. */
 int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* chunk_row,
                       int chunk, int64_t nnz, int64_t R, int64_t B, const float* x, int64_t ldx,
-                      const float* tail_feat, const float* tail_grad, int64_t ld_tail, int C, float info_scale,
-                      float* y, int64_t ldy, float* info, void* ws, void* stream);
+                      const float* tail_feat, int64_t T, float tail_scale, const float* tail_scale_dev,
+                      const float* tail_grad, int64_t ld_tail, int C, float info_scale, float* y, int64_t ldy,
+                      float* info, void* ws, void* stream);
 
 /* Dense copies of the tail entries' codewords: tail_feat[t, 4k:4k+4] = O_k[code_k(node(t)), :4],
  * tail_grad[t, 4k:4k+4] = O_k[code_k(node(t)), 4:8] (either may be NULL; D == 4, Wp == 8).  In a v2 batch graph

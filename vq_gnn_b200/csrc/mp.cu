@@ -528,13 +528,14 @@ extern "C" int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const flo
 
 extern "C" int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, const float* val,
                                  const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
-                                 const float* x, int64_t ldx, const float* tail_feat, const float* tail_grad,
-                                 int64_t ld_tail, int C, float info_scale, float* y, int64_t ldy, float* info,
-                                 void* ws, void* stream) {
+                                 const float* x, int64_t ldx, const float* tail_feat, int64_t T, float tail_scale,
+                                 const float* tail_scale_dev, const float* tail_grad, int64_t ld_tail, int C,
+                                 float info_scale, float* y, int64_t ldy, float* info, void* ws, void* stream) {
   VQ_CHECK_ARG(rowptr && x && y && (nnz == 0 || (col && val)), "mp_fwd_rows: null argument");
   VQ_CHECK_ARG(R >= B && B > 0 && B < (1ll << 31) && R < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31),
                "mp_fwd_rows: bad sizes");
   VQ_CHECK_ARG(R == B || tail_feat, "mp_fwd_rows: out-of-batch columns need the materialised feature rows (tail_feat)");
+  VQ_CHECK_ARG(T >= 0 && T >= R - B && T < (1ll << 31) && (T == 0 || tail_feat), "mp_fwd_rows: bad tail row count");
   VQ_CHECK_ARG(!info || R == B || tail_grad, "mp_fwd_rows: info needs the materialised gradient rows (tail_grad)");
   VQ_CHECK_ARG(C >= 64 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ld_tail % 4 == 0 && aligned16(x) &&
                    aligned16(y) && (!tail_feat || aligned16(tail_feat)) && (!tail_grad || aligned16(tail_grad)),
@@ -558,7 +559,7 @@ extern "C" int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, cons
   const uintptr_t xa = reinterpret_cast<uintptr_t>(x), ta = tail_feat ? reinterpret_cast<uintptr_t>(tail_feat) : xa;
   const uintptr_t base = std::min(xa, ta);
   const uint64_t x_end4 = (xa - base) / 16 + static_cast<uint64_t>(B) * (ldx / 4) + 32;
-  const uint64_t t_end4 = (ta - base) / 16 + static_cast<uint64_t>(R - B) * (ld_tail / 4) + 32;
+  const uint64_t t_end4 = (ta - base) / 16 + static_cast<uint64_t>(T) * (ld_tail / 4) + 32;
   VQ_CHECK_ARG(x_end4 < (1ull << 32) && t_end4 < (1ull << 32),
                "mp_fwd_rows: x and tail_feat must lie within 64 GB of each other (32-bit row offsets)");
   // warps per CTA x ring slots, measured at the products shape (16 M entries, C = 128): 4 x 8 -> 0.90 ms per launch,
@@ -568,8 +569,8 @@ extern "C" int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, cons
   mp_fwd_rows_kernel<NW, SLOTS><<<ceil_div(tasks, NW), NW * 32, smem, s>>>(
       rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, (int)R, (int)B, reinterpret_cast<const float4*>(base),
       static_cast<uint32_t>((xa - base) / 16), static_cast<uint32_t>(ldx / 4), static_cast<uint32_t>((ta - base) / 16),
-      static_cast<uint32_t>(ld_tail / 4), tail_grad, ld_tail, C, nslab, info_scale, y, ldy, info, w.part, w.count,
-      w.p0);
+      static_cast<uint32_t>(ld_tail / 4), tail_scale, tail_scale_dev, tail_grad, ld_tail, C, nslab, info_scale, y, ldy,
+      info, w.part, w.count, w.p0);
   VQ_LAUNCH_CHECK();
   if (n_chunks > 2) {   // rows spanning >= 3 chunks: ordered sum of their pieces
     mp_fixup_kernel<4><<<ceil_div(tasks, kMpWarps), kMpWarps * 32, 0, s>>>(rowptr, chunk_row, n_chunks, chunk, B, C,

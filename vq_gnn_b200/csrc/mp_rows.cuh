@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(NW * 32)
     mp_fwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
                        int nnz, int R, int B, const float4* __restrict__ base, uint32_t xoff4, uint32_t ldx4,
-                       uint32_t toff4, uint32_t ldt4, const float* __restrict__ tail_grad, int64_t ld_tail, int C,
-                       int nslab, float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ info,
+                       uint32_t toff4, uint32_t ldt4, float tail_scale, const float* __restrict__ tail_scale_dev,
+                       const float* __restrict__ tail_grad, int64_t ld_tail, int C, int nslab, float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ info,
                        double* ws_part, unsigned int* ws_count, float* __restrict__ py) {
   extern __shared__ __align__(128) unsigned char rows_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,12 +140,14 @@ __global__ void __launch_bounds__(NW * 32)
     uint32_t o_cur, o_nxt;
     float v_cur, v_nxt;
     const uint32_t lane_off = static_cast<uint32_t>(slab * 32);
+    const float ts = tail_scale * (tail_scale_dev ? __ldg(tail_scale_dev) : 1.f);   // weight of the codeword rows
     auto load_batch = [&](int bb, uint32_t& o_l, float& v_l) {
       const int e = bb + lane;
       o_l = 0u, v_l = 0.f;
       if (e < ee) {
         const int c = __ldg(col + e);
         v_l = __ldg(val + e);
+        if (c >= B) v_l *= ts;
         o_l = (c >= B ? toff4 + static_cast<uint32_t>(c - B) * ldt4 : xoff4 + static_cast<uint32_t>(c) * ldx4) + lane_off;
       }
     };

@@ -147,7 +147,7 @@ class VQConvFunction(torch.autograd.Function):
                 _lib.check(lib.vqgnn_mp_fwd_rows(
                     _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
                     _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
-                    _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, C, float(wu), _lib.ptr(y), y.stride(0),
+                    _lib.ptr(tail_feat), plan.T, 1.0, None, _lib.ptr(tail_grad), C, C, float(wu), _lib.ptr(y), y.stride(0),
                     _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
             else:
                 _lib.check(lib.vqgnn_mp_fwd(
@@ -180,14 +180,25 @@ class VQConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, C, device=x.device)
             nnz_t = int(plan.bwd_col.numel())
-            _lib.check(lib.vqgnn_mp_bwd(
-                _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
-                _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
-                dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
-                bank.M, bank.D, bank.Wp, _lib.ptr(ctx.tail_grad), plan.T if ctx.tail_slab else C, ctx.tail_slab,
-                0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
-                wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0),
-                _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
+            rows_ok = (not v1 and gq is None and USE_ROWS_KERNEL and ctx.tail_grad is not None and not ctx.tail_slab
+                       and C >= 64 and C % 4 == 0 and dy.stride(0) % 4 == 0)
+            if rows_ok:
+                # v2: the same lean row-gather kernel over the transposed CSR (dY rows / gradient codeword rows)
+                _lib.check(lib.vqgnn_mp_fwd_rows(
+                    _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
+                    _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, nnz_t, B, B, _lib.ptr(dy), dy.stride(0),
+                    _lib.ptr(ctx.tail_grad), plan.T, float(wu), _lib.ptr(dinfo), None, C, C, 1.0, _lib.ptr(dx),
+                    dx.stride(0),
+                    None, _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
+            else:
+                _lib.check(lib.vqgnn_mp_bwd(
+                    _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
+                    _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, int(plan.bwd_col.numel()), B, _lib.ptr(dy),
+                    dy.stride(0), _lib.ptr(plan.tail_node), _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb,
+                    bank.M, bank.D, bank.Wp, _lib.ptr(ctx.tail_grad), plan.T if ctx.tail_slab else C, ctx.tail_slab,
+                    0.0 if v1 else wu, _lib.ptr(gq), gq.stride(0) if gq is not None else 0,
+                    wu, _lib.ptr(dinfo), _lib.ptr(dx), dx.stride(0),
+                    _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
         if ctx.fire_hook:
             # the reference's hook(grad): vq.update(X_B, grad) ; c_indices[batch] = idx ; return grad
             bank.update(x, dy, plan.batch_idx)
