@@ -14,6 +14,6 @@ for c in c3 c4; do python bench.py --config $c --no-cpu-baseline > $O/bench_$c.j
 VQGNN_CUPROF=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
   --log-file $O/launches_c5_step.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graphs --sync-vq > $O/ncu_launches.log 2>&1; echo "launches rc=$?"
 VQGNN_CUPROF=1 ncu --profile-from-start off --set full --clock-control none --import-source on \
-  --kernel-name regex:"mp_fwd_async_kernel|vq_assign_tc_kernel|segsum_kernel|tail_materialize_kernel" --launch-count 8 \
+  --kernel-name regex:"mp_fwd_rows_kernel|vq_assign_tc_kernel|segsum_kernel|tail_materialize_kernel" --launch-count 14 \
   -o $O/prof_c5_step -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graphs --sync-vq > $O/ncu_full.log 2>&1; echo "ncu rc=$?"
 for f in $O/bench_*.json; do python scripts/show_bench.py $f 2>/dev/null | head -3; done

@@ -411,8 +411,8 @@ def test_v2_split_info_kernel(conv, C, slab, monkeypatch):
 
 @pytest.mark.parametrize("conv,C,power_law", [("GCN", 128, 1.4), ("SAGE", 100, 1.2), ("GCN", 64, 0.0),
                                              ("GCN", 260, 1.4)])
-def test_v2_tma_row_gather_forward(conv, C, power_law, monkeypatch):
-    """v2 layers with materialised out-of-batch rows through the TMA row-gather forward (csrc/mp_rows.cuh,
+def test_v2_row_gather_forward(conv, C, power_law, monkeypatch):
+    """v2 layers with materialised out-of-batch rows through the lean asynchronous row-gather kernel (csrc/mp_rows.cuh,
     vqgnn_mp_fwd_rows): same outputs / info / gradients / state as the oracle over three train steps; power-law graphs
     (hub rows cut by several chunk boundaries, empty rows), C below / above one 128-column slab and not a multiple of
     it; and bit-identical y to the generic kernel it replaces (same per-row order of additions)."""
