@@ -55,6 +55,18 @@ def _mp_ws(dev, nnz: int, chunk: int, C: int) -> Tensor:
                        device=dev)
 
 
+def _rows_kernel_ok(x: Tensor, tail: Optional[Tensor], C: int) -> bool:
+    """vqgnn_mp_fwd_rows takes this call: wide enough rows, 16 B aligned, and both tables inside one 32 GB window (the
+    kernel addresses rows by 32-bit offsets in 16 B units from the lower of the two base pointers)."""
+    if not USE_ROWS_KERNEL or C < 64 or C % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
+        return False
+    if tail is None:
+        return True
+    lo = min(x.data_ptr(), tail.data_ptr())
+    hi = max(x.data_ptr() + x.numel() * 4, tail.data_ptr() + tail.numel() * 4)
+    return tail.data_ptr() % 16 == 0 and hi - lo < (1 << 35)
+
+
 class VQConvFunction(torch.autograd.Function):
     """Y[:B], info_backward = conv([x ; codewords], adj)  for GCN / SAGE-Mean.
 
@@ -141,7 +153,7 @@ class VQConvFunction(torch.autograd.Function):
                 else:
                     tail_feat, tail_grad = layer.materialize_tail_rows(plan, need_info)
                 ctx.tail_grad = tail_grad
-            if (tail_feat is not None and not v1 and USE_ROWS_KERNEL and C >= 64 and C % 4 == 0 and x.stride(0) % 4 == 0
+            if (tail_feat is not None and not v1 and _rows_kernel_ok(x, tail_feat, C)
                     and (tail_grad is not None or not need_info)):
                 # materialised rows: TMA row gathers (csrc/mp_rows.cuh)
                 _lib.check(lib.vqgnn_mp_fwd_rows(
@@ -180,8 +192,8 @@ class VQConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, C, device=x.device)
             nnz_t = int(plan.bwd_col.numel())
-            rows_ok = (not v1 and gq is None and USE_ROWS_KERNEL and ctx.tail_grad is not None and not ctx.tail_slab
-                       and C >= 64 and C % 4 == 0 and dy.stride(0) % 4 == 0)
+            rows_ok = (not v1 and gq is None and ctx.tail_grad is not None and not ctx.tail_slab
+                       and _rows_kernel_ok(dy, ctx.tail_grad, C))
             if rows_ok:
                 # v2: the same lean row-gather kernel over the transposed CSR (dY rows / gradient codeword rows)
                 _lib.check(lib.vqgnn_mp_fwd_rows(
@@ -226,6 +238,12 @@ def plain_propagate(x: Tensor, adj, att_l: Optional[Tensor], att_r: Optional[Ten
     nnz = int(col.numel())
     chunks = torch.empty(max(int(lib.vqgnn_mp_num_chunks(nnz, MP_CHUNK)), 1), dtype=torch.int32, device=x.device)
     _lib.check(lib.vqgnn_mp_chunk_rows(_lib.ptr(rowptr), n, nnz, MP_CHUNK, _lib.ptr(chunks), st))
+    if att_l is None and _rows_kernel_ok(xc, None, C):     # wide rows: the lean row-gather kernel (no codeword rows)
+        _lib.check(lib.vqgnn_mp_fwd_rows(
+            _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), _lib.ptr(chunks), MP_CHUNK, nnz, n, n, _lib.ptr(xc),
+            xc.stride(0), None, 0, 1.0, None, None, 0, C, 1.0, _lib.ptr(y), y.stride(0), None,
+            _lib.ptr(_mp_ws(x.device, nnz, MP_CHUNK, C)), st))
+        return y
     if att_l is None:
         _lib.check(lib.vqgnn_mp_fwd(
             _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val), None, _lib.ptr(chunks), MP_CHUNK, nnz,
