@@ -496,13 +496,18 @@ def main():
         torch.distributed.all_reduce(cap, op=torch.distributed.ReduceOp.MAX)
         capacity = int(cap.item())
     model, head = build_model(c, dev, N, distributed, args.assign_impl, capacity)
-    model.set_async_vq_updates(not args.sync_vq)
+    per_layer = os.environ.get("VQGNN_VQ_STREAMS", "one") == "per_layer"   # measured at c5: 5.97 vs 6.00 ms, not worth 3 communicators
+    model.set_async_vq_updates(not args.sync_vq, per_layer_streams=per_layer)
     if distributed and not args.sync_vq:
         # the side-stream VQ collectives get their OWN communicator: ProcessGroupNCCL funnels every collective of a
         # group through one in-order NCCL stream, so sharing the default group would make the weight-gradient
         # allreduce on the compute stream wait for all VQ updates issued before it
-        vq_group = torch.distributed.new_group()
+        # (one per layer when the layers' updates run on their own side streams: NCCL calls on one communicator must
+        # not run concurrently)
+        vq_group = None
         for layer in model.convs:
+            if vq_group is None or per_layer:
+                vq_group = torch.distributed.new_group()
             layer.bank.process_group = vq_group
     use_graphs = not args.no_graphs
     params = list(model.parameters()) + (list(head.parameters()) if head is not None else [])

@@ -663,10 +663,13 @@ class LowRankGNN(nn.Module):
         for layer in self.convs:
             layer.check_status()
 
-    def set_async_vq_updates(self, flag: bool = True):
-        """Run the hook's VQ updates on a side stream (VQBank.async_update): they only prepare the NEXT step."""
-        for layer in self.convs:
+    def set_async_vq_updates(self, flag: bool = True, per_layer_streams: bool = False):
+        """Run the hook's VQ updates on a side stream (VQBank.async_update): they only prepare the NEXT step.
+        per_layer_streams: one side stream per layer, so the three updates of a step overlap each other as well (multi-GPU:
+        give every layer's bank its own `process_group` first)."""
+        for li, layer in enumerate(self.convs):
             layer.bank.async_update = bool(flag)
+            layer.bank.side_lane = li if per_layer_streams else 0
 
     def join_vq_updates(self):
         """Order the current stream after every pending side-stream VQ update.  Each layer's next forward does this by

@@ -62,6 +62,7 @@ class VQBank:
         # through LowRankGNN.join_vq_updates() before a CUDA-graph capture ends) orders later readers after it
         self.async_update = False
         self._pending = False
+        self.side_lane = 0            # which VQ side stream this bank's asynchronous updates run on (see side_stream)
         # 0: exact-fp32 SIMT kernel (default: bit-stable codes, the parity anchor), 1: tcgen05 3xTF32 kernel,
         # 'auto': tcgen05 when it is the faster one (M >= 512 and a packed width it supports; measured on B200:
         # 0.55 vs 0.45 ms at M = 256, 0.57 vs 0.89 at M = 1024, 0.62 vs 1.41 at M = 4096)
@@ -240,11 +241,15 @@ class VQBank:
     _SIDE = {}
 
     @classmethod
-    def side_stream(cls, dev, which: int = 0) -> "torch.cuda.Stream":
-        """ONE side stream per device (and purpose: 0 = VQ updates, 1 = tail-row prefetch), shared by every bank: the
-        updates (and their collectives) of all layers stay in program order, which is the same on every rank."""
+    def side_stream(cls, dev, which: int = 0, lane: int = 0) -> "torch.cuda.Stream":
+        """Side streams per device and purpose (0 = VQ updates, 1 = tail-row prefetch).  Lane 0 is shared by every bank:
+        the updates (and their collectives) of all layers then stay in program order, which is the same on every rank.
+        A bank with its own `side_lane` (LowRankGNN.set_async_vq_updates(per_layer_streams=True)) runs its update
+        concurrently with the other layers' -- the latency-bound small kernels of one layer (moments, sort, segmented
+        sums, finalize) fill the gaps of another layer's assignment kernel; multi-GPU this needs one communicator per
+        lane (`process_group`), NCCL calls on one communicator must not run concurrently."""
         idx = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
-        key = (idx, which)
+        key = (idx, which, lane)
         st = cls._SIDE.get(key)
         if st is None:
             st = cls._SIDE[key] = torch.cuda.Stream(device=dev)
@@ -256,7 +261,7 @@ class VQBank:
             self.run(x, g, batch_idx, True)
             return
         cur = torch.cuda.current_stream(x.device)
-        side = self.side_stream(x.device)
+        side = self.side_stream(x.device, 0, self.side_lane)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             self.run(x, g, batch_idx, True)
@@ -267,7 +272,7 @@ class VQBank:
     def join(self) -> None:
         """Order the current stream after a pending asynchronous update of this bank."""
         if self._pending:
-            torch.cuda.current_stream(self.E.device).wait_stream(self.side_stream(self.E.device))
+            torch.cuda.current_stream(self.E.device).wait_stream(self.side_stream(self.E.device, 0, self.side_lane))
             self._pending = False
 
     def check_status(self):
