@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(NW * 32)
       const int e = bb + lane;
       o_l = 0u, v_l = 0.f;
       if (e < ee) {
-        const int c = __ldg(col + e);
-        v_l = __ldg(val + e);
+        const int c = __ldcs(col + e);      // streamed once: evict-first, the L2 is for the gathered rows
+        v_l = __ldcs(val + e);
         if (c >= B) v_l *= ts;
         o_l = (c >= B ? toff4 + static_cast<uint32_t>(c - B) * ldt4 : xoff4 + static_cast<uint32_t>(c) * ldx4) + lane_off;
       }
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NW * 32)
     float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_gv = [&](int r) {
       if (info && active && r >= B && r < R)
-        gv = __ldg(reinterpret_cast<const float4*>(tail_grad + static_cast<int64_t>(r - B) * ld_tail + c0));
+        gv = __ldcs(reinterpret_cast<const float4*>(tail_grad + static_cast<int64_t>(r - B) * ld_tail + c0));
     };
     load_gv(r_pref);
 
