@@ -79,32 +79,42 @@ __device__ __forceinline__ void segsum_load(const float* __restrict__ x, int64_t
   }
 }
 
-template <int NV>
+// One task = one sub-range (<= kSegSub rows) of one (branch, codeword) segment, handled by a group of LG lanes: lane l of
+// the group takes rows l, l+LG, ... in order, then a fixed xor tree over the group -- a pure function of the inputs.
+// LG = 32 (a warp per task) when segments are long; LG = 8 when the average segment is a handful of rows (M = 4096:
+// ~5 rows per codeword), where a whole warp per segment left 27 lanes idle and the kernel was bound by the latency of
+// 131 K tiny warps.
+template <int NV, int LG>
 __global__ void __launch_bounds__(256)
     segsum_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g, int64_t ldg,
                   const float* __restrict__ scale, const float* __restrict__ shift,
                   const uint32_t* __restrict__ rows, const int32_t* __restrict__ seg_start,
                   const int32_t* __restrict__ task_off, int S, int max_tasks, int nbc, int M, int D, int Dg, int Wp,
                   int vec, float* __restrict__ stats, float* __restrict__ part) {
-  const int lane = threadIdx.x & 31;
-  const int task = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (task >= max_tasks || task >= __ldg(task_off + S)) return;
+  constexpr int GPW = 32 / LG;   // groups per warp
+  const int lane = threadIdx.x & 31, gl = lane & (LG - 1);
+  const int task = (blockIdx.x * 8 + (threadIdx.x >> 5)) * GPW + lane / LG;
+  const int n_tasks = __ldg(task_off + S);
+  const bool live = task < max_tasks && task < n_tasks;     // dead groups still take part in the shuffles below
   // largest seg with task_off[seg] <= task.  task_off[seg] = seg + (extra sub-ranges before seg), so the answer lies
   // in [task - extra_total, task]: a handful of search steps when few segments are long (the common case)
-  const int extra_total = __ldg(task_off + S) - S;
-  int lo = max(0, task - extra_total), hi = min(task, S - 1) + 1;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(task_off + mid) <= task) lo = mid;
-    else hi = mid;
+  int seg = 0, sub = 0, nsub = 1, s0 = 0, s1 = 0;
+  if (live) {
+    const int extra_total = n_tasks - S;
+    int lo = max(0, task - extra_total), hi = min(task, S - 1) + 1;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(task_off + mid) <= task) lo = mid;
+      else hi = mid;
+    }
+    seg = lo, sub = task - __ldg(task_off + seg);
+    nsub = __ldg(task_off + seg + 1) - __ldg(task_off + seg);
+    s0 = __ldg(seg_start + seg) + sub * kSegSub;
+    s1 = min(__ldg(seg_start + seg + 1), s0 + kSegSub);
   }
-  const int seg = lo, sub = task - __ldg(task_off + seg);
-  const int nsub = __ldg(task_off + seg + 1) - __ldg(task_off + seg);
   const int k = seg / M;
   const int C = nbc * D;
   const int w_use = D + (g ? Dg : 0);
-  const int s0 = __ldg(seg_start + seg) + sub * kSegSub;
-  const int s1 = min(__ldg(seg_start + seg + 1), s0 + kSegSub);
   float sc[NV * 4], sh[NV * 4];
 #pragma unroll
   for (int w = 0; w < NV * 4; ++w) {
@@ -115,11 +125,14 @@ __global__ void __launch_bounds__(256)
   float acc[NV * 4];
 #pragma unroll
   for (int w = 0; w < NV * 4; ++w) acc[w] = 0.f;
-  for (int i = s0 + lane; i < s1; i += 32)
+  for (int i = s0 + gl; i < s1; i += LG)
     segsum_load<NV>(x, ldx, g, ldg, static_cast<int64_t>(__ldg(rows + i)), k, D, Dg, w_use, vec != 0, sc, sh, acc);
 #pragma unroll
-  for (int w = 0; w < NV * 4; ++w) acc[w] = warp_sum(acc[w]);   // fixed xor tree: order independent of timing
-  if (lane != 0) return;
+  for (int w = 0; w < NV * 4; ++w) {   // fixed xor tree inside the group: order independent of timing
+#pragma unroll
+    for (int o = LG / 2; o > 0; o >>= 1) acc[w] += __shfl_xor_sync(0xffffffffu, acc[w], o);
+  }
+  if (gl != 0 || !live) return;
   if (nsub == 1) {
     float* dst = stats + static_cast<int64_t>(seg) * (Wp + 4);
 #pragma unroll
@@ -236,11 +249,19 @@ extern "C" int vqgnn_vq_segsum(const float* x, int64_t ldx, const float* g, int6
   const int vec = (D == 4 && (!g || Dg == 4) && ldx % 4 == 0 && (!g || ldg % 4 == 0) &&
                    (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (!g || (reinterpret_cast<uintptr_t>(g) & 15) == 0))
                       ? 1 : 0;
-  const int sgrid = (max_tasks + 7) / 8;
+  // lanes per task: a warp when segments are long, 8 lanes when the average (branch, codeword) segment is short
+  const bool narrow = n < 16 * S;
+  const int sgrid = narrow ? (max_tasks + 31) / 32 : (max_tasks + 7) / 8;
 #define VQ_SEGSUM(NV)                                                                                          \
   do {                                                                                                         \
-    segsum_kernel<NV><<<sgrid, 256, 0, s>>>(x, ldx, g, ldg, scale, shift, rows_out, seg_start, task_off, (int)S, \
-                                            max_tasks, nbc, M, D, g ? Dg : 0, Wp, vec, stats, part);           \
+    if (narrow)                                                                                                \
+      segsum_kernel<NV, 8><<<sgrid, 256, 0, s>>>(x, ldx, g, ldg, scale, shift, rows_out, seg_start, task_off,  \
+                                                 (int)S, max_tasks, nbc, M, D, g ? Dg : 0, Wp, vec, stats,     \
+                                                 part);                                                        \
+    else                                                                                                       \
+      segsum_kernel<NV, 32><<<sgrid, 256, 0, s>>>(x, ldx, g, ldg, scale, shift, rows_out, seg_start, task_off, \
+                                                  (int)S, max_tasks, nbc, M, D, g ? Dg : 0, Wp, vec, stats,    \
+                                                  part);                                                       \
     segsum_combine_kernel<NV><<<ceil_div(S * (NV * 4), 256), 256, 0, s>>>(seg_start, task_off, (int)S, w_use,  \
                                                                          Wp, part, stats);                     \
     count_launch(1);                                                                                           \

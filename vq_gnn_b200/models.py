@@ -55,8 +55,28 @@ def _mp_ws(dev, nnz: int, chunk: int, C: int) -> Tensor:
                        device=dev)
 
 
+def _tail_table(plan: BatchPlan, C: int) -> Tensor:
+    """[T, C] table of materialised codeword rows, allocated with B spare rows IN FRONT (`.head_rows`, a [B, C] view):
+    the row-gather kernel addresses the rows of both operands -- batch rows and codeword rows -- by 32-bit offsets from
+    one base, so the batch rows are copied next to the table (x_input = cat(x, codewords) of vq_gnn_v2/models.py:161-179,
+    literally) instead of hoping that two separate allocations of a 180 GB device land within one 64 GB window."""
+    full = torch.empty(plan.B + plan.T, C, device=plan.device)
+    t = full[plan.B:]
+    t.head_rows = full[:plan.B]
+    return t
+
+
+def _rows_operand(x: Tensor, tail: Optional[Tensor]) -> Tensor:
+    """The batch-row operand of vqgnn_mp_fwd_rows: x copied into the spare rows in front of `tail` when it has them."""
+    head = getattr(tail, 'head_rows', None)
+    if head is None or head.shape != x.shape:
+        return x
+    head.copy_(x)
+    return head
+
+
 def _rows_kernel_ok(x: Tensor, tail: Optional[Tensor], C: int) -> bool:
-    """vqgnn_mp_fwd_rows takes this call: wide enough rows, 16 B aligned, and both tables inside one 32 GB window (the
+    """vqgnn_mp_fwd_rows takes this call: wide enough rows, 16 B aligned, and both tables inside one 64 GB window (the
     kernel addresses rows by 32-bit offsets in 16 B units from the lower of the two base pointers)."""
     if not USE_ROWS_KERNEL or C < 64 or C % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
         return False
@@ -64,7 +84,7 @@ def _rows_kernel_ok(x: Tensor, tail: Optional[Tensor], C: int) -> bool:
         return True
     lo = min(x.data_ptr(), tail.data_ptr())
     hi = max(x.data_ptr() + x.numel() * 4, tail.data_ptr() + tail.numel() * 4)
-    return tail.data_ptr() % 16 == 0 and hi - lo < (1 << 35)
+    return tail.data_ptr() % 16 == 0 and hi - lo < (1 << 36) - (1 << 20)
 
 
 class VQConvFunction(torch.autograd.Function):
@@ -153,12 +173,13 @@ class VQConvFunction(torch.autograd.Function):
                 else:
                     tail_feat, tail_grad = layer.materialize_tail_rows(plan, need_info)
                 ctx.tail_grad = tail_grad
-            if (tail_feat is not None and not v1 and _rows_kernel_ok(x, tail_feat, C)
+            xr = _rows_operand(x, tail_feat) if (tail_feat is not None and not v1 and USE_ROWS_KERNEL) else x
+            if (tail_feat is not None and not v1 and _rows_kernel_ok(xr, tail_feat, C)
                     and (tail_grad is not None or not need_info)):
-                # materialised rows: TMA row gathers (csrc/mp_rows.cuh)
+                # materialised rows: lean asynchronous row gathers (csrc/mp_rows.cuh)
                 _lib.check(lib.vqgnn_mp_fwd_rows(
                     _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
-                    _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(x), x.stride(0),
+                    _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, plan.R, B, _lib.ptr(xr), xr.stride(0),
                     _lib.ptr(tail_feat), plan.T, 1.0, None, _lib.ptr(tail_grad), C, C, float(wu), _lib.ptr(y), y.stride(0),
                     _lib.ptr(info) if need_info else None, _lib.ptr(_mp_ws(dev, plan.nnz, MP_CHUNK, C)), st))
             else:
@@ -192,13 +213,13 @@ class VQConvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, C, device=x.device)
             nnz_t = int(plan.bwd_col.numel())
-            rows_ok = (not v1 and gq is None and ctx.tail_grad is not None and not ctx.tail_slab
-                       and _rows_kernel_ok(dy, ctx.tail_grad, C))
-            if rows_ok:
+            rows_cand = not v1 and gq is None and ctx.tail_grad is not None and not ctx.tail_slab and USE_ROWS_KERNEL
+            dyr = _rows_operand(dy, ctx.tail_grad) if rows_cand else dy
+            if rows_cand and _rows_kernel_ok(dyr, ctx.tail_grad, C):
                 # v2: the same lean row-gather kernel over the transposed CSR (dY rows / gradient codeword rows)
                 _lib.check(lib.vqgnn_mp_fwd_rows(
                     _lib.ptr(plan.bwd_rowptr), _lib.ptr(plan.bwd_col), _lib.ptr(plan.bwd_val),
-                    _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, nnz_t, B, B, _lib.ptr(dy), dy.stride(0),
+                    _lib.ptr(plan.chunk_rows('bwd')), plan.small_chunk, nnz_t, B, B, _lib.ptr(dyr), dyr.stride(0),
                     _lib.ptr(ctx.tail_grad), plan.T, float(wu), _lib.ptr(dinfo), None, C, C, 1.0, _lib.ptr(dx),
                     dx.stride(0),
                     None, _lib.ptr(_mp_ws(x.device, nnz_t, plan.small_chunk, C)), st))
@@ -407,8 +428,8 @@ class LowRankGNNLayer(nn.Module):
         bank, dev = self.bank, plan.device
         C = bank.nb * bank.D
         if out is None:
-            tail_feat = torch.empty(plan.T, C, device=dev)
-            tail_grad = torch.empty(plan.T, C, device=dev) if (with_grad and self.materialize_grad) else None
+            tail_feat = _tail_table(plan, C)
+            tail_grad = _tail_table(plan, C) if (with_grad and self.materialize_grad) else None
         else:
             tail_feat, tail_grad = out
         _lib.check(_lib.load().vqgnn_tail_materialize(
@@ -428,8 +449,8 @@ class LowRankGNNLayer(nn.Module):
         # the buffers are allocated on the CONSUMER's stream (its allocator pool owns them; the side stream's writes are
         # ordered before the consumer's reads by the event), so no cross-stream record_stream bookkeeping is needed
         C = self.bank.nb * self.bank.D
-        tf = torch.empty(plan.T, C, device=plan.device)
-        tg = torch.empty(plan.T, C, device=plan.device) if self.materialize_grad else None
+        tf = _tail_table(plan, C)
+        tg = _tail_table(plan, C) if self.materialize_grad else None
         side.wait_stream(torch.cuda.current_stream(plan.device))
         with torch.cuda.stream(side):
             self.materialize_tail_rows(plan, True, out=(tf, tg))
