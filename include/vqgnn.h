@@ -98,10 +98,12 @@ int vqgnn_vq_whiten(const double* sums, double count, const double* d_count, int
  * If stats != NULL the kernel instead adds z to stats[k, code, :W] and 1 to stats[k, code, Wp] with fp32 atomics in
  * its epilogue (order-dependent last bits; `stats` must be zeroed by the caller with vqgnn_fill_zero).  g == NULL selects the feature-only form (feature_update, W = D).
  * impl: 0 = exact-fp32 SIMT kernel (parity anchor; ws unused, may be NULL);
- *       1 = tcgen05 / TMEM kernel (kind::tf32, error-compensated 3xTF32, TMA-fed codebook tiles, fused
- *           argmin epilogue; packed width D+Dg in {4, 8, 9}); needs ws of vqgnn_vq_assign_workspace_bytes()
- *           bytes (the codebook re-packed into MMA tiles), 16 B aligned.  Codes may differ from impl 0 only
- *           at near-ties of the fp32 distances. */
+ *       1 = tcgen05 / TMEM kernel (kind::tf32, error-compensated 3xTF32, TMA-fed codebook tiles; packed width
+ *           D+Dg in {4, 8, 9}); needs ws of vqgnn_vq_assign_workspace_bytes() bytes (the codebook re-packed into MMA
+ *           tiles), 16 B aligned, a 16 B aligned codebook and idx != NULL.  Two kernels: the epilogue of the
+ *           tensor-core kernel keeps, per row, the running minimum over chunks of 8 codewords and the chunk it came from
+ *           (written to idx); a second kernel re-scores that chunk in fp32 from E and picks the lowest-index minimum.
+ *           Codes may differ from impl 0 only at near-ties of the fp32 distances. */
 size_t vqgnn_vq_assign_workspace_bytes(int nb, int M);
 int vqgnn_vq_assign(const float* x, int64_t ldx, const float* g, int64_t ldg, const float* scale,
                     const float* shift, const float* E, int64_t B, int nb, int M, int D, int Dg, int Wp,

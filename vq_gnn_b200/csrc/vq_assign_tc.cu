@@ -37,6 +37,7 @@ constexpr int kALbo = (kTileM / 8) * 128;      // bytes between the two 16 B K-c
 constexpr int kBLbo = (kTileN / 8) * 128;      // same for B
 constexpr int kSbo = 128;                      // bytes between 8-row core matrices
 constexpr size_t kSmemBytes = 1024 + 2 * kATileBytes + kStages * kBTileBytes + 4096;  // 165 KB: one CTA per SM
+constexpr int kCand = 8;              // the scan tracks the best chunk of kCand codewords; vq_assign_refine_kernel picks inside it
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -320,7 +321,6 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int64_t b = (item - static_cast<int64_t>(k) * row_tiles) * kTileM + rl;
       load_raw(item + 2, z2);
       // the code-table row this thread will write at the end of the item: fetch its index now, not on the tail
-      const int32_t my_node = (codes && h == 0 && b < B) ? __ldg(batch_idx + b) : 0;
       whiten(item + 1, z1);          // its loads were issued one whole item ago
       if (item + 1 < item_end) stage_a(it + 1, z1);
 
@@ -340,20 +340,19 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (lane == 0) mbar_arrive(BAR(ACC_EMPTY + buf));  // accumulator in registers: hand the buffer back early
                                                             // (one arrival per warp: 512 per-thread arrivals on one
                                                             // mbarrier were the top stall in the ncu source view)
+        // Only the minimum of every kCand-column chunk and the chunk it came from are tracked here (FMNMX3 chain + one
+        // compare / select pair, no branch).  Extracting the winning COLUMN inside the scan -- 31 FSETP/SEL pairs per
+        // 32 columns whenever ANY lane of the warp improved, i.e. for ~85 % of the chunks -- made the ALU pipe the
+        // co-bottleneck of this kernel (ncu: ALU 71 % busy; with the search stubbed out the kernel ran 30 % faster).
+        // The column is picked inside the winning chunk by vq_assign_refine_kernel.
 #pragma unroll
-        for (int cchunk = 0; cchunk < 2; ++cchunk) {
-          float v[32];
+        for (int cchunk = 0; cchunk < 64 / kCand; ++cchunk) {
+          float m = __uint_as_float(rr[kCand * cchunk]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[32 * cchunk + i]);
-          float m = v[0];
-#pragma unroll
-          for (int i = 1; i < 32; ++i) m = fminf(m, v[i]);
-          if (m < best) {  // strict: earlier (lower) codewords win ties
-            int at = 31;
-#pragma unroll
-            for (int i = 30; i >= 0; --i) at = (v[i] == m) ? i : at;
-            best = m, besti = j * kTileN + 64 * h + 32 * cchunk + at;
-          }
+          for (int i = 1; i < kCand; ++i) m = fminf(m, __uint_as_float(rr[kCand * cchunk + i]));
+          const bool better = m < best;   // strict: earlier (lower) chunks win ties
+          best = better ? m : best;
+          besti = better ? j * kTileN + 64 * h + kCand * cchunk : besti;   // first column of the chunk
         }
       }
       // ---- combine the two column halves of every row, emit code + statistics ----
@@ -366,20 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int oi = xidx[o * kTileM + rl];
           if (ob < best || (ob == best && oi < besti)) best = ob, besti = oi;
         }
-        const int code = besti;
-        if (idx) idx[b * nb + k] = static_cast<int16_t>(code);
-        if (codes) codes[static_cast<int64_t>(my_node) * codes_ld + k] = static_cast<int16_t>(code);
-        if (stats) {
-          float* dst = stats + (static_cast<int64_t>(k) * M + code) * (Wp + 4);
-#pragma unroll
-          for (int w4 = 0; w4 < (W + 3) / 4; ++w4) {
-            float t[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) t[i] = (4 * w4 + i < W) ? z[4 * w4 + i] : 0.f;
-            atomicAdd(reinterpret_cast<float4*>(dst) + w4, make_float4(t[0], t[1], t[2], t[3]));
-          }
-          atomicAdd(dst + Wp, 1.0f);
-        }
+        idx[b * nb + k] = static_cast<int16_t>(besti);   // first codeword of the winning chunk (refined below)
       }
 #pragma unroll
       for (int w = 0; w < W; ++w) z[w] = z1[w], z1[w] = z2[w];
@@ -390,6 +376,69 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   if (warp == kEpiWarps + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+// Second step of the tcgen05 assignment: inside the winning chunk of kCand codewords the column is picked by re-scoring
+// the chunk in fp32 from the codebook itself (d = ||e||^2 - 2 z.e; ||z||^2 is common to the row, z whitened with the
+// same fmaf as everywhere else), lowest index winning ties.  Against the tensor-core values this can only move the choice
+// between codewords whose distances agree to ~1e-6 relative -- well inside the near-tie band of the parity tests
+// (1e-5).  One thread per (row, branch): 2 x 16 B of the row + kCand x 32 B of the L2-resident codebook; also scatters
+// the code into the code table and, when asked, accumulates the (non-deterministic) float-atomic statistics.
+template <int W>
+__global__ void __launch_bounds__(256)
+    vq_assign_refine_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ g, int64_t ldg,
+                            const float* __restrict__ scale, const float* __restrict__ shift,
+                            const float* __restrict__ E, int64_t B, int nb, int M, int D, int Dg, int Wp,
+                            const int32_t* __restrict__ batch_idx, int16_t* __restrict__ codes, int64_t codes_ld,
+                            int16_t* __restrict__ idx, float* __restrict__ stats) {
+  constexpr int NV = (W + 3) / 4;
+  const int64_t n = B * nb;
+  const int C = nb * D;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t b = i / nb;
+    const int k = static_cast<int>(i - b * nb);
+    float z[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const int c = (w < D) ? k * D + w : C + k * Dg + (w - D);
+      const float raw = (w < D) ? __ldg(x + b * ldx + k * D + w) : __ldg(g + b * ldg + k * Dg + (w - D));
+      z[w] = fmaf(raw, __ldg(scale + c), __ldg(shift + c));
+    }
+    const int base = idx[i];
+    const float* e0 = E + (static_cast<int64_t>(k) * M + base) * Wp;
+    int code = base;
+    float dmin = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int cI = 0; cI < kCand; ++cI) {
+      if (base + cI < M) {
+        float ev[NV * 4];
+#pragma unroll
+        for (int w4 = 0; w4 < NV; ++w4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(e0 + static_cast<int64_t>(cI) * Wp) + w4);
+          ev[4 * w4] = t.x, ev[4 * w4 + 1] = t.y, ev[4 * w4 + 2] = t.z, ev[4 * w4 + 3] = t.w;
+        }
+        float c2 = 0.f, dot = 0.f;
+#pragma unroll
+        for (int w = 0; w < W; ++w) c2 = fmaf(ev[w], ev[w], c2), dot = fmaf(z[w], ev[w], dot);
+        const float d = fmaf(-2.f, dot, c2);
+        if (d < dmin) dmin = d, code = base + cI;
+      }
+    }
+    idx[i] = static_cast<int16_t>(code);
+    if (codes) codes[static_cast<int64_t>(__ldg(batch_idx + b)) * codes_ld + k] = static_cast<int16_t>(code);
+    if (stats) {
+      float* dst = stats + (static_cast<int64_t>(k) * M + code) * (Wp + 4);
+#pragma unroll
+      for (int w4 = 0; w4 < NV; ++w4) {
+        float t[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] = (4 * w4 + j < W) ? z[4 * w4 + j] : 0.f;
+        atomicAdd(reinterpret_cast<float4*>(dst) + w4, make_float4(t[0], t[1], t[2], t[3]));
+      }
+      atomicAdd(dst + Wp, 1.0f);
+    }
   }
 }
 
@@ -410,6 +459,8 @@ int launch_assign_tc(const float* x, int64_t ldx, const float* g, int64_t ldg, c
   VQ_CHECK_ARG(ws && ws_bytes >= assign_tc_workspace_bytes(nb, M), "vq_assign: tcgen05 path needs a workspace of "
                "vqgnn_vq_assign_workspace_bytes(nb, M) bytes");
   VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "vq_assign: workspace must be 16 B aligned");
+  VQ_CHECK_ARG(idx, "vq_assign: the tcgen05 path needs idx (it carries the winning chunk between its two kernels)");
+  VQ_CHECK_ARG((reinterpret_cast<uintptr_t>(E) & 15) == 0 && Wp % 4 == 0, "vq_assign: codebook must be 16 B aligned");
   const int M_pad = (M + kTileN - 1) / kTileN * kTileN;
   float* Bp = static_cast<float*>(ws);
   const int64_t n_pack = static_cast<int64_t>(nb) * M_pad;
@@ -436,6 +487,15 @@ int launch_assign_tc(const float* x, int64_t ldx, const float* g, int64_t ldg, c
     VQ_TC_LAUNCH(9, false);
   }
 #undef VQ_TC_LAUNCH
+  VQ_LAUNCH_CHECK();
+  const int rgrid = static_cast<int>(std::min<int64_t>((B * nb + 255) / 256, 32 * kNumSMs));
+#define VQ_TC_REFINE(WW)                                                                                        \
+  vq_assign_refine_kernel<WW><<<rgrid, 256, 0, s>>>(x, ldx, g, ldg, scale, shift, E, B, nb, M, D, g ? Dg : 0, Wp, \
+                                                    batch_idx, codes, codes_ld, idx, stats)
+  if (W == 4) VQ_TC_REFINE(4);
+  else if (W == 8) VQ_TC_REFINE(8);
+  else VQ_TC_REFINE(9);
+#undef VQ_TC_REFINE
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }
