@@ -736,7 +736,11 @@ def main():
         if tj:
             traffic = sum(tj["per_launch_bytes"]) / len(tj["per_launch_bytes"])
             tnote = tj.get("note")
+    traffic_rate = None
+    if traffic is not None and bound == "hbm":      # what the kernel actually pulls through HBM (ncu), next to `achieved`
+        traffic_rate = {"GBps": traffic / (avg_ms * 1e-3) / 1e9, "frac_of_peak": traffic / (avg_ms * 1e-3) / 1e9 / pk["hbm"]}
     roofline = {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                "traffic_rate": traffic_rate,
                 "frac": achieved / peak, "traffic": traffic, "traffic_note": tnote, "peak_source": pk["source"],
                 "avg_launch_ms": avg_ms, "launches_per_step": n_launch / n_attr,
                 "algorithmic_work_per_launch": per_launch_work,

@@ -173,7 +173,7 @@ int vqgnn_mp_fwd(const int32_t* rowptr, const int32_t* col, const float* val, co
  * (cp.async.bulk, <= 512 B per 128-column slab) into a per-warp ring of shared memory, so the consuming loop holds no
  * address arithmetic (csrc/mp_rows.cuh).  rows r < B: y[r] = acc; rows r >= B: info += <acc, tail_grad[r - B]>
  * (vq_gnn_v2/models.py:161-198).  Replaces vqgnn_mp_fwd(rval = NULL, tail_slab = 0, feat_scale = 1) with identical
- * per-row arithmetic; needs C >= 64, C % 4 == 0, chunk <= 256, 16 B aligned rows.  tail_feat may be NULL when R == B
+ * per-row arithmetic; needs C >= 16, C % 4 == 0, chunk <= 256, 16 B aligned rows.  tail_feat may be NULL when R == B
  * and every column is < B (plain convolution); tail_grad may be NULL when info is.  ws as for vqgnn_mp_fwd.
  * The value of an entry whose column is >= B is multiplied by tail_scale * (tail_scale_dev ? *tail_scale_dev : 1)
  * (forward: 1, NULL).  That makes the v2 BACKWARD the same call over the transposed CSR of the batch columns:
@@ -349,6 +349,18 @@ int vqgnn_gat_fwd(const int32_t* rowptr, const int32_t* col, const float* val, c
                   const float* tail_feat, int64_t ld_tail, const float* a_l, const float* a_r, const float* stat,
                   float negative_slope, float info_scale, float* y, int64_t ldy, float* den, float* info,
                   void* ws, void* stream);
+
+/* The same forward for a batch graph whose codeword rows were materialised (vqgnn_tail_materialize: tail_feat, and
+ * tail_grad when info is wanted), through the lean row-gather kernel of vqgnn_mp_fwd_rows with the GAT weights computed
+ * per entry (csrc/mp_rows.cuh).  a_l / a_r / stat from vqgnn_gat_scores over all B + T nodes.  Needs C >= 16, C % 4 == 0,
+ * chunk <= 256.  ws: 512 + 8 * ceil(ceil(nnz / chunk) * ceil(C / 128) / 4) bytes when info != NULL. */
+int vqgnn_gat_fwd_rows(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* chunk_row,
+                       int chunk, int64_t nnz, int64_t R, int64_t B, const float* x, int64_t ldx,
+                       const float* tail_feat, int64_t T, const float* tail_grad, int64_t ld_tail, int C,
+                       const float* a_l, const float* a_r, const float* stat, float negative_slope,
+                       float info_scale, float* y, int64_t ldy, float* den, float* info, void* ws, size_t ws_bytes,
+                       void* stream);
+
 
 /* Backward of vqgnn_gat_scores + vqgnn_gat_fwd given dout = d loss / d y [B, C] and dinfo (device scalar or
  * NULL = 1); `out` is the forward's y.  Outputs:

@@ -410,7 +410,7 @@ def test_v2_split_info_kernel(conv, C, slab, monkeypatch):
 
 
 @pytest.mark.parametrize("conv,C,power_law", [("GCN", 128, 1.4), ("SAGE", 100, 1.2), ("GCN", 64, 0.0),
-                                             ("GCN", 260, 1.4)])
+                                             ("GCN", 260, 1.4), ("SAGE", 52, 1.4), ("GCN", 16, 0.0)])
 def test_v2_row_gather_forward(conv, C, power_law, monkeypatch):
     """v2 layers with materialised out-of-batch rows through the lean asynchronous row-gather kernel (csrc/mp_rows.cuh,
     vqgnn_mp_fwd_rows): same outputs / info / gradients / state as the oracle over three train steps; power-law graphs
@@ -451,6 +451,39 @@ def test_v2_row_gather_forward(conv, C, power_law, monkeypatch):
     monkeypatch.setattr(Mo, "USE_ROWS_KERNEL", False)
     ye0, _ = VQConvFunction.apply(xd, None, layer, plan_e, 1.0, False)
     assert torch.equal(ye0, ye1)
+
+
+@pytest.mark.parametrize("C,power_law", [(128, 1.4), (100, 0.0), (260, 1.2), (52, 1.4)])
+def test_v2_gat_row_gather_forward(C, power_law, monkeypatch):
+    """v2 GAT with materialised codeword rows through the row-gather kernel with per-entry GAT weights
+    (vqgnn_gat_fwd_rows): outputs / info / gradients / state against the oracle over three train steps on power-law
+    graphs (rows cut by chunk boundaries), and against the generic GAT kernel on the same state."""
+    from vq_gnn_b200 import models as Mo
+    from vq_gnn_b200.gat import VQGATFunction
+    dev = torch.device("cuda:0")
+    N, B, M, D = 3000, 300, 32, 4
+    g = H.make_graph(N, 60_000, "GAT", "v2", seed=37, power_law=power_law)
+    batch_A = H.make_batch(g, B, "v2", seed=37)
+    torch.manual_seed(23)
+    layer = V.LowRankGNNLayer(*H.layer_args(C, 6, M, D, N, "GAT"), version="v2")
+    sd = {k: v.clone() for k, v in layer.state_dict().items()}
+    o = restate.OracleLayer(C, 6, M, D, N, "GAT", "v2", warm_up_flag=True).load_state_dict(sd)
+    layer = layer.to(dev)
+    layer.materialize_tail = 'force'
+    monkeypatch.setattr(Mo, "USE_ROWS_KERNEL", True)
+    x = torch.randn(B, C, generator=torch.Generator().manual_seed(3))
+    c_outs = _run_cuda(layer, batch_A, x, 3, dev, wu=0.8)
+    _compare(c_outs, _run_oracle(o, batch_A, x, 3, wu=0.8, cuda_outs=c_outs), layer, o)
+    plan = V.build_plan(H.batch_to(batch_A, dev), "GAT", N, True, dev)
+    conv = layer.conv
+    slope = float(conv.negative_slope)
+    xd = x.to(dev)
+    with torch.no_grad():
+        y1, i1 = VQGATFunction.apply(xd, conv.att_l, conv.att_r, layer, plan, 0.8, False, slope)
+        monkeypatch.setattr(Mo, "USE_ROWS_KERNEL", False)
+        y0, i0 = VQGATFunction.apply(xd, conv.att_l, conv.att_r, layer, plan, 0.8, False, slope)
+    assert H.rel_err(y1, y0) < 1e-5
+    assert abs(float(i0) - float(i1)) <= 1e-4 * max(abs(float(i0)), 1e-6), (float(i0), float(i1))
 
 
 def test_v1_tail_kernel_without_in_batch_block():

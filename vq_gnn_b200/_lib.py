@@ -44,6 +44,8 @@ _SIGNATURES = {
     "vqgnn_mp_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32,
                                vp, i64, i32, f32, f32, vp, i64, vp, i64, vp, vp, vp]),
     "vqgnn_tail_materialize": (C.c_int, [vp, i64, vp, vp, i32, i32, i32, i32, vp, vp, i64, vp]),
+    "vqgnn_gat_fwd_rows": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, i64, i32, vp, vp, vp, f32,
+                                     f32, vp, i64, vp, vp, vp, C.c_size_t, vp]),
     "vqgnn_mp_fwd_rows": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, i64, vp, i64, vp, i64, f32, vp, vp, i64, i32, f32,
                                     vp, i64, vp, vp, vp]),
     "vqgnn_mp_bwd": (C.c_int, [vp, vp, vp, vp, i32, i64, i64, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, i64,

@@ -14,7 +14,10 @@
 // SpMM for d x, and the attention-vector gradients.
 #include <math.h>
 
+#include <algorithm>
+
 #include "mp_common.cuh"
+#include "mp_rows.cuh"
 
 namespace vqgnn {
 
@@ -512,6 +515,61 @@ extern "C" int vqgnn_gat_fwd(const int32_t* rowptr, const int32_t* col, const fl
   VQ_LAUNCH_CHECK();
   const int ngrid = static_cast<int>(std::min<int64_t>((B * g.C + 255) / 256, 8 * kNumSMs));
   gat_normalize_kernel<<<ngrid, 256, 0, s>>>(B, g.C, y, ldy, den);
+  VQ_LAUNCH_CHECK();
+  return VQGNN_OK;
+}
+
+// The same forward through the lean row-gather kernel of mp_rows.cuh (materialised codeword rows, cp.async rings): the
+// GAT weights are computed once per entry by the lane that holds it.
+extern "C" int vqgnn_gat_fwd_rows(const int32_t* rowptr, const int32_t* col, const float* val,
+                                  const int32_t* chunk_row, int chunk, int64_t nnz, int64_t R, int64_t B,
+                                  const float* x, int64_t ldx, const float* tail_feat, int64_t T,
+                                  const float* tail_grad, int64_t ld_tail, int C, const float* a_l, const float* a_r,
+                                  const float* stat, float negative_slope, float info_scale, float* y, int64_t ldy,
+                                  float* den, float* info, void* ws, size_t ws_bytes, void* stream) {
+  VQ_CHECK_ARG(rowptr && x && a_l && a_r && stat && y && den && (nnz == 0 || (col && val)), "gat_fwd_rows: null argument");
+  VQ_CHECK_ARG(R >= B && B > 0 && R < (1ll << 31) && nnz >= 0 && nnz < (1ll << 31), "gat_fwd_rows: bad sizes");
+  VQ_CHECK_ARG(T >= 0 && (T == 0 || tail_feat) && (!info || R == B || tail_grad),
+               "gat_fwd_rows: needs the materialised codeword rows (tail_feat; tail_grad for info)");
+  VQ_CHECK_ARG(C >= 16 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ld_tail % 4 == 0 && aligned16(x) &&
+                   aligned16(y) && (!tail_feat || aligned16(tail_feat)) && (!tail_grad || aligned16(tail_grad)),
+               "gat_fwd_rows: needs C >= 16, C % 4 == 0 and 16 B aligned rows");
+  VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && chunk <= kRowsChunkMax && (nnz == 0 || chunk_row),
+               "gat_fwd_rows: needs chunk_row with chunk <= 256");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = zero_rows(y, B, C, ldy, s)) return rc;
+  VQ_CUDA(cudaMemsetAsync(den, 0, sizeof(float) * B, s));
+  const int n_chunks = static_cast<int>((nnz + chunk - 1) / chunk);
+  if (n_chunks == 0) {
+    if (info) VQ_CUDA(cudaMemsetAsync(info, 0, sizeof(float), s));
+    return VQGNN_OK;
+  }
+  const int nslab = ceil_div(C, 128);
+  const int64_t tasks = static_cast<int64_t>(n_chunks) * nslab;
+  constexpr int NW = kRowsWarps, SLOTS = kRowsSlots;
+  const int grid = ceil_div(tasks, NW);
+  // workspace: [count 256 B][per-block info partials]
+  VQ_CHECK_ARG(!info || (ws && ws_bytes >= 512 + static_cast<size_t>(grid) * 8), "gat_fwd_rows: workspace too small");
+  char* wp = ws ? reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~static_cast<uintptr_t>(255)) : nullptr;
+  unsigned int* ws_count = reinterpret_cast<unsigned int*>(wp);
+  double* ws_part = reinterpret_cast<double*>(wp + 256);
+  if (info) VQ_CUDA(cudaMemsetAsync(ws_count, 0, 16, s));
+  const uintptr_t xa = reinterpret_cast<uintptr_t>(x), ta = tail_feat ? reinterpret_cast<uintptr_t>(tail_feat) : xa;
+  const uintptr_t base = std::min(xa, ta);
+  const uint64_t x_end4 = (xa - base) / 16 + static_cast<uint64_t>(B) * (ldx / 4) + 32;
+  const uint64_t t_end4 = (ta - base) / 16 + static_cast<uint64_t>(T) * (ld_tail / 4) + 32;
+  VQ_CHECK_ARG(x_end4 < (1ull << 32) && t_end4 < (1ull << 32),
+               "gat_fwd_rows: x and tail_feat must lie within 64 GB of each other (32-bit row offsets)");
+  const size_t smem = sizeof(RowsWarpSmem<SLOTS>) * NW;
+  RowsGat gp{a_l, a_r, stat, negative_slope, den};
+  mp_fwd_rows_kernel<NW, SLOTS, true><<<grid, NW * 32, smem, s>>>(
+      rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, (int)R, (int)B, reinterpret_cast<const float4*>(base),
+      static_cast<uint32_t>((xa - base) / 16), static_cast<uint32_t>(ldx / 4), static_cast<uint32_t>((ta - base) / 16),
+      static_cast<uint32_t>(ld_tail / 4), 1.0f, nullptr, tail_grad, ld_tail, C, nslab, info_scale, y, ldy, info, ws_part,
+      ws_count, nullptr, gp);
+  VQ_LAUNCH_CHECK();
+  const int ngrid = static_cast<int>(std::min<int64_t>((B * C + 255) / 256, 8 * kNumSMs));
+  gat_normalize_kernel<<<ngrid, 256, 0, s>>>(B, C, y, ldy, den);
   VQ_LAUNCH_CHECK();
   return VQGNN_OK;
 }

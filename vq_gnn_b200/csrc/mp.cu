@@ -537,9 +537,9 @@ extern "C" int vqgnn_mp_fwd_rows(const int32_t* rowptr, const int32_t* col, cons
   VQ_CHECK_ARG(R == B || tail_feat, "mp_fwd_rows: out-of-batch columns need the materialised feature rows (tail_feat)");
   VQ_CHECK_ARG(T >= 0 && T >= R - B && T < (1ll << 31) && (T == 0 || tail_feat), "mp_fwd_rows: bad tail row count");
   VQ_CHECK_ARG(!info || R == B || tail_grad, "mp_fwd_rows: info needs the materialised gradient rows (tail_grad)");
-  VQ_CHECK_ARG(C >= 64 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ld_tail % 4 == 0 && aligned16(x) &&
+  VQ_CHECK_ARG(C >= 16 && C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ld_tail % 4 == 0 && aligned16(x) &&
                    aligned16(y) && (!tail_feat || aligned16(tail_feat)) && (!tail_grad || aligned16(tail_grad)),
-               "mp_fwd_rows: needs C >= 64, C % 4 == 0 and 16 B aligned rows");
+               "mp_fwd_rows: needs C >= 16, C % 4 == 0 and 16 B aligned rows");
   VQ_CHECK_ARG(chunk > 0 && chunk % 32 == 0 && chunk <= kRowsChunkMax && (nnz == 0 || chunk_row),
                "mp_fwd_rows: needs chunk_row (vqgnn_mp_chunk_rows) with chunk <= 256");
   VQ_CHECK_ARG(ws || nnz == 0, "mp_fwd_rows: needs a workspace of vqgnn_mp_workspace_bytes(nnz, chunk, C) bytes");

@@ -98,14 +98,26 @@ __device__ __forceinline__ void rows_info_reduce(double part, double* ws_part, u
 
 // base: a 16 B aligned address below both tables; xoff4 / toff4: offsets of x / tail_feat from it in 16 B units;
 // ldx4 / ldt4: row strides in 16 B units.  Every gathered piece must lie below base + 2^32 * 16 B (checked on the host).
-template <int NW, int SLOTS>
+// GAT (vq_gnn_v2/convs.py:165-266 with vq_softmax == un-normalised exp): the value of entry (i, j) becomes
+// val * exp(leaky_relu((a_col[j] + a_row[i]) / sigma)), sigma = sqrt(stat[0]^2 + 1) sqrt(stat[1]^2 + 1), and the sum of
+// the weights of a batch row goes to den[i] (the ones column of x_input).  Rows cut by a chunk boundary accumulate with
+// REDs / float atomics here (the GAT path is not bit-reproducible).
+struct RowsGat {
+  const float* a_col;
+  const float* a_row;
+  const float* stat;
+  float slope;
+  float* den;
+};
+
+template <int NW, int SLOTS, bool GAT = false>
 __global__ void __launch_bounds__(NW * 32)
     mp_fwd_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks, int chunk,
                        int nnz, int R, int B, const float4* __restrict__ base, uint32_t xoff4, uint32_t ldx4,
                        uint32_t toff4, uint32_t ldt4, float tail_scale, const float* __restrict__ tail_scale_dev,
                        const float* __restrict__ tail_grad, int64_t ld_tail, int C, int nslab, float info_scale, float* __restrict__ y, int64_t ldy, float* __restrict__ info,
-                       double* ws_part, unsigned int* ws_count, float* __restrict__ py) {
+                       double* ws_part, unsigned int* ws_count, float* __restrict__ py, RowsGat gat = RowsGat()) {
   extern __shared__ __align__(128) unsigned char rows_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   RowsWarpSmem<SLOTS>& S = reinterpret_cast<RowsWarpSmem<SLOTS>*>(rows_smem)[warp];
@@ -141,6 +153,11 @@ __global__ void __launch_bounds__(NW * 32)
     float v_cur, v_nxt;
     const uint32_t lane_off = static_cast<uint32_t>(slab * 32);
     const float ts = tail_scale * (tail_scale_dev ? __ldg(tail_scale_dev) : 1.f);   // weight of the codeword rows
+    float inv_sigma = 1.f, den_acc = 0.f;
+    if constexpr (GAT) {
+      const float ml = __ldg(gat.stat), mr = __ldg(gat.stat + 1);
+      inv_sigma = 1.f / (sqrtf(ml * ml + 1.f) * sqrtf(mr * mr + 1.f));
+    }
     auto load_batch = [&](int bb, uint32_t& o_l, float& v_l) {
       const int e = bb + lane;
       o_l = 0u, v_l = 0.f;
@@ -148,6 +165,22 @@ __global__ void __launch_bounds__(NW * 32)
         const int c = __ldcs(col + e);      // streamed once: evict-first, the L2 is for the gathered rows
         v_l = __ldcs(val + e);
         if (c >= B) v_l *= ts;
+        if constexpr (GAT) {
+          // the row of this entry = the row whose end is the first marked position at or after it (else the row that
+          // continues past the chunk)
+          const int p = e - eb;
+          int w = p >> 5;
+          uint32_t m = S.endmask[w] >> (p & 31);
+          int q = p - 1;
+          if (m == 0u) {
+            q = (w + 1) * 32 - 1;
+            for (++w; w < kRowsChunkMax / 32 && (m = S.endmask[w]) == 0u; ++w) q += 32;
+          }
+          const int row = m ? S.row_of[q + __ffs(m)] : rowL;
+          float ev = (__ldg(gat.a_col + c) + __ldg(gat.a_row + row)) * inv_sigma;
+          ev = ev > 0.f ? ev : gat.slope * ev;
+          v_l = v_l * expf(ev);
+        }
         o_l = (c >= B ? toff4 + static_cast<uint32_t>(c - B) * ldt4 : xoff4 + static_cast<uint32_t>(c) * ldx4) + lane_off;
       }
     };
@@ -187,11 +220,20 @@ __global__ void __launch_bounds__(NW * 32)
 
     auto flush = [&](int r, bool whole) {
       if (r != r_pref) load_gv(r);
+      if constexpr (GAT) {
+        if (r < B && slab == 0 && lane == 0) {
+          if (whole) gat.den[r] = den_acc;
+          else atomicAdd(gat.den + r, den_acc);
+        }
+        den_acc = 0.f;
+      }
       if (active) {
         if (r < B) {
           float* yp = y + static_cast<int64_t>(r) * ldy + c0;
           if (whole) {
             st_vec<4>(yp, acc);
+          } else if constexpr (GAT) {
+            red_vec<4>(yp, acc);
           } else {
             const int kind = piece_kind(false, __ldg(rowptr + r), __ldg(rowptr + r + 1), eb, chunk);
             if (kind == kPieceRed) red_vec<4>(yp, acc);
@@ -227,6 +269,7 @@ __global__ void __launch_bounds__(NW * 32)
               const int s = g * G + u;              // ring slot (a constant after unrolling)
               if (j0 + s < cnt) {
                 const float v = __shfl_sync(0xffffffffu, v_cur, j0 + s);
+                if constexpr (GAT) den_acc += v;
                 if (active) {
                   const float4 a = S.ring[s * 32 + lane];
                   acc[0] = fmaf(v, a.x, acc[0]), acc[1] = fmaf(v, a.y, acc[1]);

@@ -39,7 +39,8 @@ class VQGATFunction(torch.autograd.Function):
         if (plan.T > 0 and bank.D == 4 and bank.Wp == 8
                 and (layer.materialize_tail == 'force' or (layer.materialize_tail and auto))):
             # every out-of-batch node's codewords gathered once into dense rows (see models.VQConvFunction)
-            tail_feat = torch.empty(plan.T, C, device=dev)
+            from .models import _tail_table           # [T, C] with B spare rows in front (see models._tail_table)
+            tail_feat = _tail_table(plan, C)
             tail_grad = torch.empty(plan.T, C, device=dev) if plan.training else None
             _lib.check(lib.vqgnn_tail_materialize(
                 _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
@@ -53,6 +54,24 @@ class VQGATFunction(torch.autograd.Function):
         den = torch.empty(B, device=dev)
         need_info = plan.training
         info = torch.zeros((), device=dev)
+        from .models import _rows_kernel_ok, _rows_operand
+        xr = _rows_operand(x, tail_feat) if tail_feat is not None else x
+        if (tail_feat is not None and (tail_grad is not None or not need_info) and _rows_kernel_ok(xr, tail_feat, C)
+                and MP_CHUNK <= 256):
+            # materialised rows: the lean row-gather kernel with per-entry GAT weights (csrc/mp_rows.cuh)
+            nck = (plan.nnz + MP_CHUNK - 1) // MP_CHUNK
+            wsb = 1024 + 8 * (nck * ((C + 127) // 128) // 4 + 2)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if need_info else None
+            _lib.check(lib.vqgnn_gat_fwd_rows(
+                _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
+                _lib.ptr(plan.chunk_rows('fwd')), MP_CHUNK, plan.nnz, R, B, _lib.ptr(xr), xr.stride(0),
+                _lib.ptr(tail_feat), plan.T, _lib.ptr(tail_grad), C, C, _lib.ptr(a_l), _lib.ptr(a_r), _lib.ptr(stat),
+                float(slope), float(wu), _lib.ptr(y), y.stride(0), _lib.ptr(den),
+                _lib.ptr(info) if need_info else None, _lib.ptr(ws), wsb if need_info else 0, st))
+            ctx.layer, ctx.plan, ctx.wu, ctx.fire_hook, ctx.slope = layer, plan, float(wu), fire_hook, float(slope)
+            ctx.att_shape = att_l.shape
+            ctx.save_for_backward(x, al, ar, a_l, a_r, stat, y, den)
+            return y, info
         ws = torch.empty(8, dtype=torch.float64, device=dev) if need_info else None
         _lib.check(lib.vqgnn_gat_fwd(
             _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),

@@ -78,7 +78,7 @@ def _rows_operand(x: Tensor, tail: Optional[Tensor]) -> Tensor:
 def _rows_kernel_ok(x: Tensor, tail: Optional[Tensor], C: int) -> bool:
     """vqgnn_mp_fwd_rows takes this call: wide enough rows, 16 B aligned, and both tables inside one 64 GB window (the
     kernel addresses rows by 32-bit offsets in 16 B units from the lower of the two base pointers)."""
-    if not USE_ROWS_KERNEL or C < 64 or C % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
+    if not USE_ROWS_KERNEL or C < 16 or C % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
         return False
     if tail is None:
         return True
