@@ -277,6 +277,174 @@ __global__ void __launch_bounds__(kMpWarps * 32)
   walk_rows<false>(t.eb, t.ee, t.row0, R, rowptr, col, val, nullptr, B, cb.tail_node, lane, pol, body, flush);
 }
 
+// (B1, lean) the same score gradients in the style of mp_rows.cuh, for materialised codeword rows: Xin[j] rows arrive
+// through the warp's cp.async ring; per entry the lane's four columns give a partial dot product that is parked in a
+// 32 x 33 shared-memory tile, and once per 32-entry batch lane L sums column L (conflict-free) -- two instructions per
+// entry instead of a five-step shuffle reduction -- and finishes ITS entry: de = s * w * lrelu', one float atomic onto
+// ds_l[col] and one onto ds_r[row].  dY'[i] (the row operand) is prefetched one row ahead.
+constexpr int kEdgeWarps = 4;
+struct __align__(128) GatEdgeSmem {
+  RowsWarpSmem<kRowsSlots> r;
+  float red[32 * 33];
+};
+
+__global__ void __launch_bounds__(kEdgeWarps * 32)
+    gat_bwd_edge_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                             const float* __restrict__ val, const int32_t* __restrict__ chunk_row, int n_chunks,
+                             int chunk, int nnz, int R, int B, const float4* __restrict__ base, uint32_t xoff4,
+                             uint32_t ldx4, uint32_t toff4, uint32_t ldt4, const float* __restrict__ tail_grad,
+                             int64_t ld_tail, int C, int nslab, const float* __restrict__ a_l,
+                             const float* __restrict__ a_r, const float* __restrict__ stat, float slope,
+                             const float* __restrict__ dyn, int64_t lddyn, const float* __restrict__ dden,
+                             float tail_scale, const float* __restrict__ dinfo, float* __restrict__ ds_l,
+                             float* __restrict__ ds_r) {
+  constexpr int SLOTS = kRowsSlots, G = SLOTS / 4;
+  extern __shared__ __align__(128) unsigned char edge_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  GatEdgeSmem& S = reinterpret_cast<GatEdgeSmem*>(edge_smem)[warp];
+  const int64_t task = static_cast<int64_t>(blockIdx.x) * kEdgeWarps + warp;
+  if (task >= static_cast<int64_t>(n_chunks) * nslab) return;
+  const int slab = static_cast<int>(task / n_chunks);
+  const int ch = static_cast<int>(task - static_cast<int64_t>(slab) * n_chunks);
+  const int c0 = slab * 128 + lane * 4;
+  const bool active = c0 < C;
+  const int eb = ch * chunk, ee = min(eb + chunk, nnz);
+  const int row0 = __ldg(chunk_row + ch);
+  const int rowL = ch + 1 < n_chunks ? __ldg(chunk_row + ch + 1) : R - 1;
+  const uint32_t slot_s = rows_smem_u32(S.r.ring) + lane * 16;
+  const float ml = __ldg(stat), mr = __ldg(stat + 1);
+  const float inv_sigma = 1.f / (sqrtf(ml * ml + 1.f) * sqrtf(mr * mr + 1.f));
+  const float ts = tail_scale * (dinfo ? __ldg(dinfo) : 1.f);
+
+  if (lane < kRowsChunkMax / 32) S.r.endmask[lane] = 0u;
+  __syncwarp();
+  for (int r = row0 + lane; r <= rowL; r += 32) {
+    const int rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+    if (re > rs && re > eb && re <= ee) {
+      const int p = re - 1 - eb;
+      atomicOr(&S.r.endmask[p >> 5], 1u << (p & 31));
+      S.r.row_of[p] = r;
+    }
+  }
+  __syncwarp();
+
+  // per-lane entry state of two batches: ring offset, column, row, d e / d s factor, ones-column term
+  uint32_t o_cur, o_nxt;
+  int c_cur, c_nxt, r_cur, r_nxt;
+  float f_cur, f_nxt, d_cur, d_nxt;
+  const uint32_t lane_off = static_cast<uint32_t>(slab * 32);
+  auto load_batch = [&](int bb, uint32_t& o_l, int& c_l, int& r_l, float& f_l, float& d_l) {
+    const int e = bb + lane;
+    o_l = 0u, c_l = 0, r_l = 0, f_l = 0.f, d_l = 0.f;
+    if (e < ee) {
+      const int c = __ldg(col + e);
+      const float v = __ldg(val + e);
+      o_l = (c >= B ? toff4 + static_cast<uint32_t>(c - B) * ldt4 : xoff4 + static_cast<uint32_t>(c) * ldx4) + lane_off;
+      const int p = e - eb;
+      int w = p >> 5;
+      uint32_t m = S.r.endmask[w] >> (p & 31);
+      int q = p - 1;
+      if (m == 0u) {
+        q = (w + 1) * 32 - 1;
+        for (++w; w < kRowsChunkMax / 32 && (m = S.r.endmask[w]) == 0u; ++w) q += 32;
+      }
+      const int row = m ? S.r.row_of[q + __ffs(m)] : rowL;
+      float ev = (__ldg(a_l + c) + __ldg(a_r + row)) * inv_sigma;
+      const float dl = ev > 0.f ? 1.f : slope;
+      ev = ev > 0.f ? ev : slope * ev;
+      c_l = c, r_l = row;
+      f_l = v * expf(ev) * dl;
+      d_l = (slab == 0 && row < B) ? __ldg(dden + row) : 0.f;
+    }
+  };
+  auto refill = [&](auto s0_tag, int j0, uint32_t o_src, int bb) {
+    constexpr int S0 = decltype(s0_tag)::value;
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int j = j0 + u + SLOTS;
+      const uint32_t o = __shfl_sync(0xffffffffu, o_src, j & 31) + lane;
+      if (bb + j < ee && active) rows_cp_async16(slot_s + (S0 + u) * kRowsSlotBytes, base + o);
+    }
+    rows_cp_commit();
+  };
+  load_batch(eb, o_cur, c_cur, r_cur, f_cur, d_cur);
+  load_batch(eb + 32, o_nxt, c_nxt, r_nxt, f_nxt, d_nxt);
+  constexpr_for<0, 4>([&](auto gt) {
+    constexpr int g = decltype(gt)::value;
+    refill(IntC<g * G>{}, g * G - SLOTS, o_cur, eb);
+  });
+
+  // dY'[r] for the lane's four columns: dYn[r] for a batch row, tail_scale * dinfo * Gq[r] otherwise
+  auto load_dy = [&](int r) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && r >= 0 && r < R) {
+      if (r < B) {
+        t = __ldg(reinterpret_cast<const float4*>(dyn + static_cast<int64_t>(r) * lddyn + c0));
+      } else {
+        t = __ldg(reinterpret_cast<const float4*>(tail_grad + static_cast<int64_t>(r - B) * ld_tail + c0));
+        t.x *= ts, t.y *= ts, t.z *= ts, t.w *= ts;
+      }
+    }
+    return t;
+  };
+  int row_now = __shfl_sync(0xffffffffu, r_cur, 0);
+  float4 dy = load_dy(row_now);
+  int r_pref = row_now + 1;
+  float4 dy_pref = load_dy(r_pref);
+
+  int batch = 0;
+  for (int bb = eb; bb < ee; bb += 32, ++batch) {
+    const int cnt = min(32, ee - bb);
+    const uint32_t em = S.r.endmask[batch];
+#pragma unroll 1
+    for (int j0 = 0; j0 < 32; j0 += SLOTS) {
+      const uint32_t emr = em >> j0;
+      const uint32_t o_src = (j0 + SLOTS < 32) ? o_cur : o_nxt;
+      constexpr_for<0, 4>([&](auto gt) {
+        constexpr int g = decltype(gt)::value;
+        rows_cp_wait<3>();
+        if (j0 + g * G < cnt) {
+#pragma unroll
+          for (int u = 0; u < G; ++u) {
+            const int sI = g * G + u;
+            if (j0 + sI < cnt) {
+              float part = 0.f;
+              if (active) {
+                const float4 a = S.r.ring[sI * 32 + lane];
+                part = fmaf(dy.x, a.x, fmaf(dy.y, a.y, fmaf(dy.z, a.z, dy.w * a.w)));
+              }
+              S.red[(j0 + sI) * 33 + lane] = part;
+              if ((emr >> sI) & 1u) {     // the row ends here: the next entry starts the next non-empty row
+                const int jn = j0 + sI + 1;
+                const int rn = __shfl_sync(0xffffffffu, jn < 32 ? r_cur : r_nxt, jn & 31);
+                dy = (rn == r_pref) ? dy_pref : load_dy(rn);
+                r_pref = rn + 1;
+                dy_pref = load_dy(r_pref);
+              }
+            }
+          }
+        }
+        refill(IntC<g * G>{}, j0 + g * G, o_src, bb);
+      });
+    }
+    __syncwarp();
+    {   // lane L finishes entry L of the batch
+      float sdot = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) sdot += S.red[lane * 33 + l];
+      if (lane < cnt) {
+        const float de = (sdot + d_cur) * f_cur;
+        atomicAdd(ds_l + c_cur, de);
+        atomicAdd(ds_r + r_cur, de);
+      }
+    }
+    __syncwarp();
+    o_cur = o_nxt, c_cur = c_nxt, r_cur = r_nxt, f_cur = f_nxt, d_cur = d_nxt;
+    load_batch(bb + 64, o_nxt, c_nxt, r_nxt, f_nxt, d_nxt);
+  }
+  rows_cp_wait<0>();
+}
+
 // (B2) d x from the aggregation: dx[j] = sum_i w_ij dY'[i]  over the transposed CSR (columns j < B)
 template <int VEC>
 __global__ void __launch_bounds__(kMpWarps * 32)
@@ -606,7 +774,34 @@ extern "C" int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const fl
   VQ_CUDA(cudaMemsetAsync(datt_l, 0, sizeof(float) * (C + 1), s));
   VQ_CUDA(cudaMemsetAsync(datt_r, 0, sizeof(float) * (C + 1), s));
   const int n_chunks = static_cast<int>((nnz + chunk - 1) / chunk);
-  if (n_chunks > 0) {
+  // materialised codeword rows within one 64 GB window of x: the lean edge kernel
+  bool edge_rows = false;
+  if (n_chunks > 0 && g.vec4 && tail_feat && tail_grad && C % 4 == 0 && chunk <= kRowsChunkMax && ldx % 4 == 0 &&
+      lddyn % 4 == 0 && ld_tail % 4 == 0 && aligned16(x) && aligned16(dyn) && aligned16(tail_feat) &&
+      aligned16(tail_grad)) {
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(x), ta = reinterpret_cast<uintptr_t>(tail_feat);
+    const uintptr_t base = std::min(xa, ta);
+    const uint64_t x_end4 = (xa - base) / 16 + static_cast<uint64_t>(B) * (ldx / 4) + 32;
+    const uint64_t t_end4 = (ta - base) / 16 + static_cast<uint64_t>(R - B) * (ld_tail / 4) + 32;
+    if (x_end4 < (1ull << 32) && t_end4 < (1ull << 32)) {
+      edge_rows = true;
+      const int nslab = ceil_div(C, 128);
+      const int64_t tasks = static_cast<int64_t>(n_chunks) * nslab;
+      const size_t smem = sizeof(GatEdgeSmem) * kEdgeWarps;
+      static bool attr_set = false;
+      if (!attr_set) {
+        VQ_CUDA(cudaFuncSetAttribute(gat_bwd_edge_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+      }
+      gat_bwd_edge_rows_kernel<<<ceil_div(tasks, kEdgeWarps), kEdgeWarps * 32, smem, s>>>(
+          rowptr, col, val, chunk_row, n_chunks, chunk, (int)nnz, (int)R, (int)B, reinterpret_cast<const float4*>(base),
+          static_cast<uint32_t>((xa - base) / 16), static_cast<uint32_t>(ldx / 4),
+          static_cast<uint32_t>((ta - base) / 16), static_cast<uint32_t>(ld_tail / 4), tail_grad, ld_tail, C, nslab, a_l,
+          a_r, stat, negative_slope, dyn, lddyn, dden, tail_scale, dinfo, ds_l, ds_r);
+      VQ_LAUNCH_CHECK();
+    }
+  }
+  if (n_chunks > 0 && !edge_rows) {
     const int grid = ceil_div(static_cast<int64_t>(n_chunks) * g.nslab, kMpWarps);
 #define VQ_GAT_EDGE(VEC)                                                                                      \
   gat_bwd_edge_kernel<VEC><<<grid, kMpWarps * 32, 0, s>>>(rowptr, col, val, chunk_row, n_chunks, chunk,        \
@@ -618,10 +813,34 @@ extern "C" int vqgnn_gat_bwd(const int32_t* rowptr, const int32_t* col, const fl
 #undef VQ_GAT_EDGE
     VQ_LAUNCH_CHECK();
   }
+  bool node_rows = false;
   if (dx) {
     if (int rc = zero_rows(dx, B, C, lddx, s)) return rc;
     const int bn_chunks = static_cast<int>((bnnz + chunk - 1) / chunk);
-    if (bn_chunks > 0) {
+    // (B2, lean) the transposed weighted SpMM through the row-gather kernel: rows = batch columns j (score a_l), entries =
+    // target rows i (score a_r), operand rows dYn[i] / tail_scale * dinfo * Gq[i]
+    if (bn_chunks > 0 && edge_rows && lddx % 4 == 0 && aligned16(dx)) {
+      const uintptr_t xa = reinterpret_cast<uintptr_t>(dyn), ta = reinterpret_cast<uintptr_t>(tail_grad);
+      const uintptr_t base = std::min(xa, ta);
+      const uint64_t x_end4 = (xa - base) / 16 + static_cast<uint64_t>(B) * (lddyn / 4) + 32;
+      const uint64_t t_end4 = (ta - base) / 16 + static_cast<uint64_t>(R - B) * (ld_tail / 4) + 32;
+      if (x_end4 < (1ull << 32) && t_end4 < (1ull << 32)) {
+        node_rows = true;
+        constexpr int NW = kRowsWarps, SLOTS = kRowsSlots;
+        const int nslab = ceil_div(C, 128);
+        const int64_t tasks = static_cast<int64_t>(bn_chunks) * nslab;
+        const size_t smem = sizeof(RowsWarpSmem<SLOTS>) * NW;
+        RowsGat gp{a_r, a_l, stat, negative_slope, nullptr};
+        mp_fwd_rows_kernel<NW, SLOTS, true><<<ceil_div(tasks, NW), NW * 32, smem, s>>>(
+            browptr, brow, bval, bchunk_row, bn_chunks, chunk, (int)bnnz, (int)B, (int)B,
+            reinterpret_cast<const float4*>(base), static_cast<uint32_t>((xa - base) / 16),
+            static_cast<uint32_t>(lddyn / 4), static_cast<uint32_t>((ta - base) / 16),
+            static_cast<uint32_t>(ld_tail / 4), tail_scale, dinfo, nullptr, ld_tail, C, nslab, 1.0f, dx, lddx, nullptr,
+            nullptr, nullptr, nullptr, gp);
+        VQ_LAUNCH_CHECK();
+      }
+    }
+    if (bn_chunks > 0 && !node_rows) {
       const int grid = ceil_div(static_cast<int64_t>(bn_chunks) * g.nslab, kMpWarps);
 #define VQ_GAT_NODE(VEC)                                                                                     \
   gat_bwd_node_kernel<VEC><<<grid, kMpWarps * 32, 0, s>>>(browptr, brow, bval, bchunk_row, bn_chunks, chunk,  \

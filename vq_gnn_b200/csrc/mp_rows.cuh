@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(NW * 32)
     auto flush = [&](int r, bool whole) {
       if (r != r_pref) load_gv(r);
       if constexpr (GAT) {
-        if (r < B && slab == 0 && lane == 0) {
+        if (r < B && slab == 0 && lane == 0 && gat.den) {
           if (whole) gat.den[r] = den_acc;
           else atomicAdd(gat.den + r, den_acc);
         }

@@ -41,7 +41,7 @@ class VQGATFunction(torch.autograd.Function):
             # every out-of-batch node's codewords gathered once into dense rows (see models.VQConvFunction)
             from .models import _tail_table           # [T, C] with B spare rows in front (see models._tail_table)
             tail_feat = _tail_table(plan, C)
-            tail_grad = torch.empty(plan.T, C, device=dev) if plan.training else None
+            tail_grad = _tail_table(plan, C) if plan.training else None     # its spare rows receive dYn in the backward
             _lib.check(lib.vqgnn_tail_materialize(
                 _lib.ptr(plan.tail_node), plan.T, _lib.ptr(bank.codes), _lib.ptr(bank.O), bank.nb, bank.M, bank.D,
                 bank.Wp, _lib.ptr(tail_feat), _lib.ptr(tail_grad), C, st))
@@ -94,11 +94,18 @@ class VQGATFunction(torch.autograd.Function):
         R, dev = plan.R, x.device
         dy = dy.contiguous().float()
         dinfo = dinfo.contiguous().float()
-        dyn = torch.empty(B, C, device=dev)
+        dyn = getattr(ctx.tail[1], 'head_rows', None) if ctx.tail[1] is not None else None
+        if dyn is None or dyn.shape != x.shape:
+            dyn = torch.empty(B, C, device=dev)
         dden = torch.empty(B, device=dev)
         ds_l, ds_r = torch.empty(R, device=dev), torch.empty(R, device=dev)
         datt_l, datt_r = torch.empty(C + 1, device=dev), torch.empty(C + 1, device=dev)
         dx = torch.empty(B, C, device=dev) if ctx.needs_input_grad[0] else None
+        xo = x
+        if ctx.tail[0] is not None:      # batch rows next to the codeword rows: one 32-bit-offset window (models._tail_table)
+            from .models import _rows_operand
+            xo = _rows_operand(x, ctx.tail[0])
+        x_keep, x = x, xo
         _lib.check(lib.vqgnn_gat_bwd(
             _lib.ptr(plan.fwd_rowptr), _lib.ptr(plan.fwd_col), _lib.ptr(plan.fwd_val),
             _lib.ptr(plan.chunk_rows('fwd')), plan.nnz, R,
@@ -112,7 +119,7 @@ class VQGATFunction(torch.autograd.Function):
             _lib.ptr(dx), dx.stride(0) if dx is not None else 0, _lib.ptr(datt_l), _lib.ptr(datt_r), st))
         if ctx.fire_hook:
             # the hook sees d loss / d (un-normalised conv output)[:B, :C]  (vq_gnn_v2/models.py:181-185)
-            bank.update(x, dyn, plan.batch_idx)
+            bank.update(x_keep, dyn, plan.batch_idx)
         return dx, datt_l.view(ctx.att_shape), datt_r.view(ctx.att_shape), None, None, None, None, None
 
 
