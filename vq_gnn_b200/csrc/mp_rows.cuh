@@ -6,15 +6,18 @@
 // accumulation and the same order-independent piece scheme as mp_fwd_kernel, but
 //   * a warp owns a small ring of row slots (kRowsSlots = 8 x 512 B) in four cp.async groups; entry n of the chunk uses
 //     slot n % 8, and a group is refilled (16 B per lane, one commit per group, one wait per group) as soon as it has
-//     been consumed: 6..8 rows in flight per warp, 28 warps per SM.  Measured: small rings with many warps beat deep
-//     rings (32 slots x 12 warps: 1.54 ms, 8 slots x 28 warps: 0.90 ms per launch at the products shape);
+//     been consumed: 6..8 rows in flight per warp, 32 warps per SM.  Measured: small rings with many warps beat deep
+//     rings (32 slots x 12 warps: 1.54 ms, 8 slots x 32 warps: 0.82 ms per launch at the products shape);
 //   * every lane precomputes the 32-bit offset (in 16 B units from a common base) of ITS entry's row once per batch, so
 //     issuing a row is SHFL + IADD + IMAD.WIDE + LDGSTS;
 //   * row ends are marked once per task from the row pointers (a 256-bit mask + the row id of every end position in
-//     shared memory), so the fully unrolled consuming loop costs one predicate test per entry instead of the sequential
-//     row walk: SHFL (value) + LDS.128 + 4 FFMA + test;
+//     shared memory), so the consuming loop (unrolled over one ring round) costs one predicate test per entry instead
+//     of the sequential row walk: SHFL (value) + LDS.128 + 4 FFMA + test;
 //   * the gradient codeword row of an out-of-batch row (the other operand of info_backward) is read from the
 //     materialised table and prefetched one row ahead.
+// The same kernel, with the entry value replaced by the GAT weight (template flag GAT), is the GAT forward and the GAT
+// backward's transposed SpMM (csrc/gat.cu).  Now DRAM bound at the products shape (ncu: 63 % of the DRAM peak, the
+// 460 MB row table does not fit the L2).
 // Tried first and dropped: one `cp.async.bulk` (TMA) per row completing on an mbarrier -- correct but slower than the
 // kernel it was to replace (1.59 vs 1.36 ms): 512 B bulk copies are bound by the per-SM TMA request rate (~1 per 29 clk).
 //
