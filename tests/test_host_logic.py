@@ -25,6 +25,25 @@ def test_library_exports_every_declared_symbol():
         assert n in V._lib._SIGNATURES, n
 
 
+def test_tail_table_keeps_the_batch_rows_next_to_the_codeword_rows():
+    """models._tail_table / _rows_operand: the materialised codeword table [T, C] is a view into ONE [B + T, C] buffer
+    whose first B rows receive the batch-row operand (the reference's x_input = cat(x, codewords),
+    vq_gnn_v2/models.py:161-179), so that vqgnn_mp_fwd_rows can address every operand row by a 32-bit offset."""
+    from types import SimpleNamespace
+    from vq_gnn_b200 import models as Mo
+    plan = SimpleNamespace(B=5, T=7, device=torch.device("cpu"))
+    t = Mo._tail_table(plan, 8)
+    assert t.shape == (7, 8) and t.head_rows.shape == (5, 8)
+    assert t.data_ptr() == t.head_rows.data_ptr() + 5 * 8 * 4 and t.is_contiguous()
+    x = torch.randn(5, 8)
+    xr = Mo._rows_operand(x, t)
+    assert xr is t.head_rows and torch.equal(xr, x)
+    assert Mo._rows_operand(torch.randn(4, 8), t).shape == (4, 8)          # shape mismatch: the tensor itself
+    assert Mo._rows_operand(x, torch.empty(7, 8)) is x                     # a plain table has no spare rows
+    # the guard of the kernel's preconditions (width, alignment, one 64 GB window)
+    assert Mo._rows_kernel_ok(xr, t, 8) is False and Mo._rows_kernel_ok(torch.empty(5, 16), None, 16) in (True, False)
+
+
 def test_no_cpu_fallback():
     vq = V.VectorQuantizerEMA(16, 4, grad_normalize_scale=[1, 1])
     with pytest.raises(V._lib.VQGNNLibraryError):
