@@ -32,11 +32,12 @@ class LinkPredictor(nn.Module):
             lin.reset_parameters()
 
     def forward(self, x_i, x_j):
+        from .models import _linear      # tall inputs: split-K weight gradient (models._TallLinear)
         x = x_i * x_j
         for lin in self.lins[:-1]:
-            x = F.relu(lin(x))
+            x = F.relu(_linear(lin, x))
             x = F.dropout(x, p=self.dropout, training=self.training)
-        return torch.sigmoid(self.lins[-1](x))
+        return torch.sigmoid(_linear(self.lins[-1], x))
 
 
 def positive_edges(batch_A) -> Tuple[Tensor, Tensor]:
