@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define VQGNN_ABI_VERSION 2
+#define VQGNN_ABI_VERSION 3
 
 #define VQGNN_OK 0
 #define VQGNN_ERR_ARCH (-1)      /* device is not sm_100 */

@@ -159,7 +159,7 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here == header/library mismatch: fail loudly
         fn.restype, fn.argtypes = res, args
-    if lib.vqgnn_abi_version() != 2:
+    if lib.vqgnn_abi_version() != 3:
         raise VQGNNLibraryError("libvqgnn.so ABI version mismatch")
     _lib = _Proxy(lib)
     return _lib
